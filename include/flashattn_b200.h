@@ -1,0 +1,154 @@
+/*
+ * flashattn_b200.h -- C ABI of the B200-native fused-attention libraries.
+ *
+ * Three shared libraries are built by compile_cuda.sh under minitorch/cuda_kernels/,
+ * with the SAME file names and the SAME legacy symbols the reference loads through
+ * ctypes (reference: minitorch/cuda_kernel_ops.py:26-29), so the reference's own
+ * cuda_kernel_ops.py binds them unchanged:
+ *
+ *   flashattention_kernel.so   replaces src/flashattention_kernel.cu
+ *   softmax_kernel.so          replaces src/softmax_kernel.cu
+ *   layernorm_kernel.so        replaces src/layernorm_kernel.cu
+ *
+ * Everything is plain pointers and ints: no torch / numpy types cross this boundary.
+ * Tensors are row-major; "host" pointers are ordinary CPU memory (numpy storage),
+ * "dev" pointers are CUDA device memory.  Legacy symbols keep the reference's `void`
+ * return type; they never exit() or throw -- the outcome is read with fa_last_status().
+ */
+#ifndef FLASHATTN_B200_H_
+#define FLASHATTN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fa_stream_t; /* == cudaStream_t; NULL = default stream */
+
+/* ---- status (all three libraries) ------------------------------------------------- */
+enum { FA_OK = 0, FA_ERR_INVALID = 1, FA_ERR_UNSUPPORTED = 2, FA_ERR_CUDA = 3 };
+int fa_last_status(void);          /* status of the most recent call into this library */
+const char* fa_last_error(void);   /* human-readable message for it ("" when FA_OK)     */
+
+/* ---- device-memory / timing utilities (all three libraries) ----------------------- */
+int fa_device_count(void);
+int fa_set_device(int dev);
+void* fa_malloc(size_t bytes);                 /* NULL on failure */
+void* fa_malloc_host(size_t bytes);            /* pinned host memory */
+int fa_free(void* dptr);
+int fa_free_host(void* hptr);
+int fa_memset(void* dptr, int byte, size_t bytes);
+int fa_h2d(void* dst_dev, const void* src_host, size_t bytes);
+int fa_d2h(void* dst_host, const void* src_dev, size_t bytes);
+int fa_sync(void);                             /* cudaDeviceSynchronize */
+void* fa_event_create(void);
+int fa_event_record(void* ev, fa_stream_t s);
+float fa_event_elapsed_ms(void* ev_start, void* ev_stop); /* synchronises on ev_stop */
+int fa_event_destroy(void* ev);
+int fa_flush_l2(void);                         /* overwrite a >L2-sized scratch buffer */
+
+/* =====================================================================================
+ * flashattention_kernel.so
+ * ===================================================================================== */
+enum { FA_DTYPE_F32 = 0, FA_DTYPE_BF16 = 1 };
+/* Arithmetic used by the legacy host-pointer entry points (their ABI is fp32 only):
+ *   FA_MODE_FP32: fp32 SIMT kernels, <=1e-5 of the composed reference (default);
+ *   FA_MODE_BF16: inputs rounded to bf16 on device, tcgen05 tensor-core kernels
+ *                 (head_dim 64/128), fp32 accumulation, <=2e-2 max-abs.
+ * Also settable with env MINITORCH_FA_MODE=fp32|bf16 read at load time. */
+enum { FA_MODE_FP32 = 0, FA_MODE_BF16 = 1 };
+void fa_set_mode(int mode);
+int fa_get_mode(void);
+
+/* Legacy ABI -- identical to the reference's
+ *   src/flashattention_kernel.cu:259 launch_flashattention_forward
+ *   src/flashattention_kernel.cu:352 launch_flashattention_backward
+ *   src/flashattention_kernel.cu:694 launch_flashattention_forward_causal
+ *   src/flashattention_kernel.cu:761 launch_flashattention_backward_causal
+ * Q,K,V,O,dO,dQ,dK,dV: host fp32 (B,nh,N,d) contiguous; l,m: host fp32 (B,nh,N).
+ * scale = 1/sqrt(d) applied inside; K is NOT transposed; m = row max of the scaled
+ * scores, l = sum exp(s - m).  Outputs are fully overwritten. */
+void launch_flashattention_forward(float* Q, float* K, float* V, float* O, float* l, float* m, int B, int nh,
+                                   int N, int d);
+void launch_flashattention_forward_causal(float* Q, float* K, float* V, float* O, float* l, float* m, int B,
+                                          int nh, int N, int d);
+void launch_flashattention_backward(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV,
+                                    float* dO, float* l, float* m, int B, int nh, int N, int d);
+void launch_flashattention_backward_causal(float* Q, float* K, float* V, float* O, float* dQ, float* dK,
+                                           float* dV, float* dO, float* l, float* m, int B, int nh, int N,
+                                           int d);
+/* Same, plus key padding (additive (B,N) host mask, LightSeq semantics of
+ * src/softmax_kernel.cu:27-33, may be NULL) -- the reference has no flash+padding entry. */
+void launch_flashattention_forward_masked(float* Q, float* K, float* V, float* O, float* l, float* m,
+                                          const float* key_mask, int causal, int B, int nh, int N, int d);
+void launch_flashattention_backward_masked(float* Q, float* K, float* V, float* O, float* dQ, float* dK,
+                                           float* dV, float* dO, float* l, float* m, const float* key_mask,
+                                           int causal, int B, int nh, int N, int d);
+
+/* Device-pointer API (no copies, asynchronous on `stream`).
+ * dtype selects the element type of Q,K,V,O,dO,dQ,dK,dV (m,l are always fp32).
+ * Element (b,h,n,x) of every 4-D tensor lives at  b*stride_b + h*stride_h + n*stride_n + x
+ * (in elements); pass 0,0,0 for the contiguous (B,nh,N,d) layout.  (B,N,nh,d) storage --
+ * what MultiHeadAttention.project_to_query_key_value produces before its permute,
+ * minitorch/modules_transfomer.py:87-100 -- is stride_b=N*nh*d, stride_h=d, stride_n=nh*d.
+ * kv_len: optional int32[B] (keys >= kv_len[b] are padding); key_mask: optional fp32 (B,N)
+ * additive mask.  Returns FA_OK or an error code (message via fa_last_error()). */
+typedef struct {
+  int B, H, N, d;
+  int dtype;      /* FA_DTYPE_* */
+  int causal;     /* 0/1 */
+  long long stride_b, stride_h, stride_n; /* elements; all 0 => contiguous (B,H,N,d) */
+  const int* kv_len;       /* device int32[B] or NULL */
+  const float* key_mask;   /* device fp32 (B,N) additive or NULL */
+} fa_attn_desc;
+
+int fa_flash_fwd_dev(const fa_attn_desc* desc, const void* Q, const void* K, const void* V, void* O, float* m,
+                     float* l, fa_stream_t stream);
+int fa_flash_bwd_dev(const fa_attn_desc* desc, const void* Q, const void* K, const void* V, const void* O,
+                     const void* dO, const float* m, const float* l, void* dQ, void* dK, void* dV,
+                     fa_stream_t stream);
+/* fp32 <-> bf16 element conversion on device (n elements). */
+int fa_cast_f32_to_bf16_dev(const float* src, void* dst_bf16, size_t n, fa_stream_t stream);
+int fa_cast_bf16_to_f32_dev(const void* src_bf16, float* dst, size_t n, fa_stream_t stream);
+/* Algorithmic FLOPs of one call (4*B*H*N*Nk*d fwd, 10*... bwd; causal halves; kv_len host
+ * array optional) -- the figure bench.py divides by the measured time. */
+double fa_attn_flops(int B, int H, int N, int d, int causal, const int* kv_len_host, int backward);
+
+/* =====================================================================================
+ * softmax_kernel.so   (reference: src/softmax_kernel.cu:233, :345)
+ * ===================================================================================== */
+/* In-place masked row softmax of inp (B,nhead,from_len,to_len) fp32; attn_mask (B,to_len)
+ * additive or NULL; mask_future masks j>i; denominator is sum+1e-8 like the reference. */
+void launch_attn_softmax(float* inp, const float* attn_mask, int batch_size, int nhead, int from_len,
+                         int to_len, bool mask_future, fa_stream_t stream);
+/* In-place: out_grad <- soft_inp * (out_grad - sum_j out_grad*soft_inp), rows x softmax_len. */
+void launch_attn_softmax_bw(float* out_grad, const float* soft_inp, int rows, int softmax_len,
+                            fa_stream_t stream);
+int fa_attn_softmax_dev(float* inp, const float* attn_mask, int batch_size, int nhead, int from_len, int to_len,
+                        int mask_future, fa_stream_t stream);
+int fa_attn_softmax_bw_dev(float* out_grad, const float* soft_inp, long long rows, int softmax_len,
+                           fa_stream_t stream);
+
+/* =====================================================================================
+ * layernorm_kernel.so   (reference: src/layernorm_kernel.cu:101, :370)
+ * ===================================================================================== */
+/* vars receives var+1e-8 and the backward adds 1e-8 again, exactly like the reference
+ * (src/layernorm_kernel.cu:70, :229, :310). */
+void launch_layernorm(float* ln_res, float* vars, float* means, const float* inp, const float* scale,
+                      const float* bias, int batch_size, int hidden_dim, fa_stream_t stream);
+void launch_layernorm_bw(float* gamma_grad, float* betta_grad, float* inp_grad, const float* out_grad,
+                         const float* inp, const float* gamma, const float* betta, const float* vars,
+                         const float* means, int batch_size, int hidden_dim, fa_stream_t stream_1,
+                         fa_stream_t stream_2);
+int fa_layernorm_dev(float* ln_res, float* vars, float* means, const float* inp, const float* scale,
+                     const float* bias, long long rows, int hidden_dim, fa_stream_t stream);
+int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, const float* out_grad,
+                        const float* inp, const float* gamma, const float* betta, const float* vars,
+                        const float* means, long long rows, int hidden_dim, fa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLASHATTN_B200_H_ */

@@ -1,0 +1,17 @@
+"""B200-native fused attention path behind minitorch's CudaKernelOps operator surface.
+
+Layout:
+  csrc/                CUDA sources (tcgen05/TMA attention, fp32 attention, softmax, layernorm) + C ABI
+  compile_cuda.sh      builds minitorch/cuda_kernels/{flashattention,softmax,layernorm}_kernel.so for sm_100a
+  cuda_kernel_ops.py   CudaKernelOps: the reference's fused-op entry points over ctypes
+  tensor.py            stand-alone host tensor + FlashAttention / Attn_Softmax / LayerNorm autograd nodes
+  device.py            device-resident buffers + the *_dev entry points (bench / sharded runs)
+"""
+from . import _lib, device
+from ._lib import FlashAttnError
+from .cuda_kernel_ops import CudaKernelOps
+from .tensor import (Attn_Softmax, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
+                     default_backend, tensor_from_numpy)
+
+__all__ = ["CudaKernelOps", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
+           "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device"]

@@ -1,0 +1,374 @@
+// Flash-attention forward for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM.
+//
+// One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong so the
+// tensor pipe works on one tile while the other tile's softmax runs on the CUDA cores.
+//   warps 0-3 : softmax group 0 (thread t of warp w owns query row 32w+t of Q tile 0)
+//   warps 4-7 : softmax group 1 (Q tile 1)
+//   warp  8   : TMA producer (Q tiles once; K,V tiles through an NSTAGE ring)
+//   warp  9   : tcgen05.mma issuer (one lane) + TMEM allocation
+//   warps 10-11: idle (they complete the third warpgroup so setmaxnreg can move its registers
+//               to the softmax groups: 208 regs/thread there, 96 here)
+// TMEM (512 columns): S0 | S1 (128 fp32 columns each), O0 | O1 (D columns each).  P (bf16)
+// overwrites the first 64 columns of its S tile and is consumed directly from TMEM as the
+// A operand of the PV MMA, so P never touches shared memory.
+// Per KV tile j and Q tile g the issuer runs   O_g += P_g(j) V_j ;  S_g = Q_g K_{j+1}^T
+// and the softmax group g turns S_g into P_g: row max, lazy rescale of O_g (only when the max
+// grew by more than 2^8), exp2 with the 1/sqrt(d)*log2(e) scale folded into one FFMA, row sum.
+// One thread owns one row, so the row reductions need no cross-thread traffic at all.
+// Masks: causal (tiles above the diagonal are skipped, only the diagonal tile is masked),
+// key padding as kv_len[b] (tiles beyond it are skipped) or a generic additive (B,N) mask.
+#pragma once
+#include "ptx.cuh"
+
+namespace fa {
+namespace sm100 {
+
+struct FwdParams {
+  int B, H, N;
+  const int* kv_len;      // device int32[B] or nullptr
+  const float* key_mask;  // device fp32 (B,N) or nullptr (MASKMODE 2)
+  void* O;                // (B,H,N,D) OutT with strides below
+  long long o_sb, o_sh, o_sn;
+  float* M;               // (B,H,N) row max of scaled scores
+  float* L;               // (B,H,N) sum exp(s - m)
+  float scale;            // 1/sqrt(d)
+  float scale_log2;       // scale * log2(e)
+};
+
+template <int D, int PMODE>
+struct FwdCfg {
+  static constexpr int NCHUNK = D / 64;            // 128-byte swizzle chunks per row
+  static constexpr int CHUNK_BYTES = 128 * 128;    // [128 rows][64 bf16]
+  static constexpr int TILE_BYTES = NCHUNK * CHUNK_BYTES;
+  static constexpr int P_BYTES = (PMODE == 1) ? 2 * CHUNK_BYTES : 0;  // debug: P through smem
+  static constexpr int NSTAGE = (PMODE == 1) ? 2 : ((D == 128) ? 5 : 8);
+  static constexpr int SMEM_TILES = 2 * TILE_BYTES + NSTAGE * TILE_BYTES + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
+  static constexpr int NTHREADS = 384;
+};
+
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* r) {
+  uint32_t u[32];
+  tmem_ld32(taddr, u);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_row32(OutT* dst, const float* v);
+template <>
+__device__ __forceinline__ void store_row32<float>(float* dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <>
+__device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    reinterpret_cast<uint4*>(dst)[i] = u;
+  }
+}
+
+// MASKMODE: 0 none (N-ragged only), 1 kv_len[b], 2 additive key mask (B,N)
+template <int D, bool CAUSAL, int MASKMODE, typename OutT, int PMODE>
+__global__ void __launch_bounds__(384, 1)
+    fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  using Cfg = FwdCfg<D, PMODE>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][TILE_BYTES]
+  uint8_t* sKV = smem + 2 * Cfg::TILE_BYTES;            // [NSTAGE][TILE_BYTES]
+  uint8_t* sP = sKV + NSTAGE * Cfg::TILE_BYTES;         // [2][P_BYTES] (PMODE 1 only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* kv_full = bars + 2;            // [NSTAGE]
+  uint64_t* kv_empty = kv_full + NSTAGE;   // [NSTAGE]
+  uint64_t* s_full = kv_empty + NSTAGE;    // [2]
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* o_done = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // causal: longest blocks first
+  const int h = blockIdx.y, b = blockIdx.z;
+  int kv_end = p.N;
+  if (MASKMODE == 1) kv_end = min(kv_end, max(__ldg(p.kv_len + b), 0));
+  const int nkv_total = (kv_end + 127) >> 7;
+  int r0[2], nkv[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    r0[g] = qb * 256 + g * 128;
+    nkv[g] = (r0[g] >= p.N) ? 0 : (CAUSAL ? min(nkv_total, (r0[g] >> 7) + 1) : nkv_total);
+  }
+  const int nk = max(nkv[0], nkv[1]);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+   reg_dealloc<96>();
+   if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (nkv[g] > 0) {
+          mbar_expect_tx(&q_full[g], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < Cfg::NCHUNK; ++c)
+            tma_load_4d(sQ + g * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQ, &q_full[g], c * 64, r0[g], h, b);
+        }
+      }
+      for (int t = 0; t < 2 * nk; ++t) {
+        const int stage = t % NSTAGE, it = t / NSTAGE;
+        mbar_wait(&kv_empty[stage], (it & 1) ^ 1);
+        mbar_expect_tx(&kv_full[stage], Cfg::TILE_BYTES);
+        const CUtensorMap* tm = (t & 1) ? &tmV : &tmK;
+        uint8_t* dst = sKV + stage * Cfg::TILE_BYTES;
+#pragma unroll
+        for (int c = 0; c < Cfg::NCHUNK; ++c)
+          tma_load_4d(dst + c * Cfg::CHUNK_BYTES, tm, &kv_full[stage], c * 64, (t >> 1) * 128, h, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && nk > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
+      const uint32_t tS[2] = {tmem_base + Cfg::S_COL0, tmem_base + Cfg::S_COL1};
+      const uint32_t tO[2] = {tmem_base + Cfg::O_COL0, tmem_base + Cfg::O_COL1};
+      auto stage_addr = [&](int t) { return smem_u32(sKV + (t % NSTAGE) * Cfg::TILE_BYTES); };
+      auto wait_full = [&](int t) {
+        mbar_wait(&kv_full[t % NSTAGE], (t / NSTAGE) & 1);
+        tc_fence_after();
+      };
+      // S_g = Q_g K^T : A = Q (K-major), B = K tile (K-major), 16 head-dim elements per MMA
+      auto issue_qk = [&](int g, int t) {
+        const uint32_t qa = smem_u32(sQ + g * Cfg::TILE_BYTES), ka = stage_addr(t);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32;
+          mma_ss(tS[g], make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk, k > 0);
+        }
+      };
+      // O_g += P_g V : A = P (TMEM, or smem K-major in PMODE 1), B = V tile (MN-major), 16 keys per MMA
+      auto issue_pv = [&](int g, int t, bool acc) {
+        const uint32_t va = stage_addr(t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t bdesc = make_smem_desc(va + k * 2048, Cfg::CHUNK_BYTES, 1024);
+          if (PMODE == 0) {
+            mma_ts(tO[g], tS[g] + k * 8, bdesc, idesc_pv, (acc || k > 0) ? 1u : 0u);
+          } else {
+            const uint32_t pa = smem_u32(sP + g * Cfg::P_BYTES) + (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32;
+            mma_ss(tO[g], make_smem_desc(pa, 16, 1024), bdesc, idesc_pv, (acc || k > 0) ? 1u : 0u);
+          }
+        }
+      };
+      wait_full(0);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (nkv[g] > 0) {
+          mbar_wait(&q_full[g], 0);
+          tc_fence_after();
+          issue_qk(g, 0);
+          mma_commit(&s_full[g]);
+        }
+      }
+      mma_commit(&kv_empty[0]);
+      for (int j = 0; j < nk; ++j) {
+        const int tv = 2 * j + 1, tk = 2 * j + 2;
+        wait_full(tv);
+        bool k_ready = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (j < nkv[g]) {
+            mbar_wait(&p_full[g], j & 1);
+            tc_fence_after();
+            issue_pv(g, tv, j > 0);
+            mma_commit(&o_done[g]);
+            if (j + 1 < nkv[g]) {
+              if (!k_ready) {
+                wait_full(tk);
+                k_ready = true;
+              }
+              issue_qk(g, tk);
+              mma_commit(&s_full[g]);
+            }
+          }
+        }
+        mma_commit(&kv_empty[tv % NSTAGE]);
+        if (j + 1 < nk) mma_commit(&kv_empty[tk % NSTAGE]);
+      }
+    }
+    __syncwarp();
+   }  // warps 10, 11 idle
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    reg_alloc<208>();
+    const int g = warp >> 2, w = warp & 3;
+    const int row = r0[g] + w * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
+    const uint32_t tS = lane_base + (g ? Cfg::S_COL1 : Cfg::S_COL0);
+    const uint32_t tO = lane_base + (g ? Cfg::O_COL1 : Cfg::O_COL0);
+    const float sc = (MASKMODE == 2) ? 1.0f : p.scale_log2;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float* mrow = (MASKMODE == 2) ? p.key_mask + static_cast<long long>(b) * p.N : nullptr;
+    OutT* orow = reinterpret_cast<OutT*>(p.O) + b * p.o_sb + h * p.o_sh + static_cast<long long>(row) * p.o_sn;
+    const long long stat_idx = (static_cast<long long>(b) * p.H + h) * p.N + row;
+
+    if (nkv[g] == 0) {
+      if (row < p.N) {  // no visible key at all (kv_len == 0): O = 0, m = -inf, l = 0
+        float z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) store_row32<OutT>(orow + 32 * c, z);
+        p.M[stat_idx] = -INFINITY;
+        p.L[stat_idx] = 0.f;
+      }
+    } else {
+      float m_used = -INFINITY, m_true = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nkv[g]; ++j) {
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        float s[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32f(tS + 32 * c, &s[32 * c]);
+        tmem_wait_ld();
+        const int k0 = j * 128;
+        if (MASKMODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) {
+            const float mv = (k0 + i < p.N) ? __ldg(mrow + k0 + i) : 0.f;
+            s[i] = fmaf(s[i], p.scale_log2, mv * LOG2E);
+          }
+        }
+        const bool need_mask = (k0 + 128 > kv_end) || (CAUSAL && (k0 + 127 > r0[g]));
+        if (need_mask) {
+          int limit = kv_end - k0;
+          if (CAUSAL) limit = min(limit, row - k0 + 1);
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= limit) s[i] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+        m_true = fmaxf(m_true, mx);
+        if (j == 0) {
+          m_used = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          // lazy rescale: only when some row of this warp grew by more than 2^8
+          const bool want = (mx - m_used) * sc > 8.0f;
+          if (__any_sync(0xffffffffu, want)) {
+            const float m_new = fmaxf(m_used, mx);
+            const float factor = ex2_approx((m_used - m_new) * sc);
+            m_used = m_new;
+            l_run *= factor;
+            mbar_wait(&o_done[g], (j - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t u[32];
+              tmem_ld32(tO + 32 * c, u);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * factor);
+              tmem_st32(tO + 32 * c, u);
+            }
+          }
+        }
+        const float neg_m = -m_used * sc;
+        float rs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          s[i] = ex2_approx(fmaf(s[i], sc, neg_m));
+          rs += s[i];
+        }
+        l_run += rs;
+        if (PMODE == 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[64 * c + 2 * i], s[64 * c + 2 * i + 1]);
+            tmem_st32(tS + 32 * c, pk);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+        } else {
+          // debug path: P -> shared memory in the K-major 128B-swizzled layout of an A operand
+          uint8_t* prow = sP + g * Cfg::P_BYTES + (w * 32 + lane) * 128;
+          const int rx = (w * 32 + lane) & 7;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            uint4 v;
+            v.x = pack_bf16x2(s[8 * u], s[8 * u + 1]);
+            v.y = pack_bf16x2(s[8 * u + 2], s[8 * u + 3]);
+            v.z = pack_bf16x2(s[8 * u + 4], s[8 * u + 5]);
+            v.w = pack_bf16x2(s[8 * u + 6], s[8 * u + 7]);
+            *reinterpret_cast<uint4*>(prow + (u >> 3) * Cfg::CHUNK_BYTES + (((u & 7) ^ rx) << 4)) = v;
+          }
+          tmem_wait_st();
+          fence_proxy_async_smem();
+          tc_fence_before();
+        }
+        mbar_arrive(&p_full[g]);
+      }
+      // epilogue: O / l -> global, statistics
+      mbar_wait(&o_done[g], (nkv[g] - 1) & 1);
+      tc_fence_after();
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        float o[32];
+        tmem_ld32f(tO + 32 * c, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= inv;
+        if (row < p.N) store_row32<OutT>(orow + 32 * c, o);
+      }
+      if (row < p.N) {
+        const float m_out = (MASKMODE == 2) ? m_true * (1.0f / LOG2E) : m_true * p.scale;
+        p.M[stat_idx] = m_out;
+        p.L[stat_idx] = l_run * ex2_approx((m_used - m_true) * sc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace sm100
+}  // namespace fa

@@ -1,0 +1,518 @@
+// flashattention_kernel.so -- C ABI of the fused attention path (see include/flashattn_b200.h).
+//
+// Replaces the reference's src/flashattention_kernel.cu (launchers :259, :352, :694, :761).
+// Two arithmetic modes sit behind the same entry points:
+//   FA_MODE_BF16 / FA_DTYPE_BF16 : flash_fwd_sm100.cuh / flash_bwd_sm100.cuh -- TMA + tcgen05 + TMEM
+//   FA_MODE_FP32 / FA_DTYPE_F32  : flash_fp32.cuh -- fp32 CUDA-core kernels, any N and head dim
+// The legacy host-pointer symbols stage through a grow-only device pool (no per-call
+// cudaMalloc/cudaFree as in the reference, :280-324) and never exit() the process.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#include "host_common.cuh"
+#include "flash_fp32.cuh"
+#include "flash_fwd_sm100.cuh"
+#include "flash_bwd_sm100.cuh"
+
+namespace fa {
+
+static int g_mode = -1;  // resolved lazily from MINITORCH_FA_MODE
+static int g_pmode = 0;  // debug: FA_PMODE=1 routes P through shared memory instead of TMEM
+
+static int current_mode() {
+  if (g_mode < 0) {
+    const char* e = getenv("MINITORCH_FA_MODE");
+    g_mode = (e && (!strcmp(e, "bf16") || !strcmp(e, "BF16"))) ? FA_MODE_BF16 : FA_MODE_FP32;
+    const char* pm = getenv("FA_PMODE");
+    g_pmode = (pm && pm[0] == '1') ? 1 : 0;
+  }
+  return g_mode;
+}
+
+// --------------------------------------------------------------------------------------------
+// TMA descriptors.  cuTensorMapEncodeTiled is fetched through the runtime so the library does
+// not link against libcuda.
+// --------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D map over a (B,H,N,d) tensor with element strides (sb, sh, sn, 1); box = [box_rows][box_cols] x 1 x 1,
+// 128-byte swizzle, out-of-bounds rows read as zero / are not written.
+static int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, int B, int H, int N, int d,
+                     long long sb, long long sh, long long sn, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sn * esize, (cuuint64_t)sh * esize, (cuuint64_t)sb * esize};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d; base %p d %d N %d strides %lld %lld %lld)",
+                     (int)r, base, d, N, sn, sh, sb);
+  return FA_OK;
+}
+
+struct Strides {
+  long long sb, sh, sn;
+};
+static Strides resolve_strides(const fa_attn_desc* a) {
+  if (a->stride_b == 0 && a->stride_h == 0 && a->stride_n == 0)
+    return {(long long)a->H * a->N * a->d, (long long)a->N * a->d, (long long)a->d};
+  return {a->stride_b, a->stride_h, a->stride_n};
+}
+
+static int validate(const fa_attn_desc* a, const char* who) {
+  if (!a) return set_error(FA_ERR_INVALID, "%s: null descriptor", who);
+  if (a->B <= 0 || a->H <= 0 || a->N <= 0 || a->d <= 0)
+    return set_error(FA_ERR_INVALID, "%s: bad shape B=%d H=%d N=%d d=%d", who, a->B, a->H, a->N, a->d);
+  if (a->dtype != FA_DTYPE_F32 && a->dtype != FA_DTYPE_BF16)
+    return set_error(FA_ERR_INVALID, "%s: unknown dtype %d", who, a->dtype);
+  if (a->H > 65535 || a->B > 65535) return set_error(FA_ERR_UNSUPPORTED, "%s: B and H must be <= 65535", who);
+  return FA_OK;
+}
+
+static AttnParams make_params(const fa_attn_desc* a) {
+  Strides s = resolve_strides(a);
+  AttnParams p;
+  p.B = a->B, p.H = a->H, p.N = a->N, p.d = a->d;
+  p.causal = a->causal ? 1 : 0;
+  p.sb = s.sb, p.sh = s.sh, p.sn = s.sn;
+  p.kv_len = a->kv_len;
+  p.key_mask = a->key_mask;
+  p.scale = 1.0f / sqrtf((float)a->d);
+  return p;
+}
+
+static bool tc_supported(const fa_attn_desc* a) {
+  if (a->dtype != FA_DTYPE_BF16) return false;
+  if (a->d != 64 && a->d != 128) return false;
+  Strides s = resolve_strides(a);
+  return (s.sn % 8 == 0) && (s.sh % 8 == 0) && (s.sb % 8 == 0);  // TMA strides: multiples of 16 bytes
+}
+
+// ------------------------------------------------------------------------------------- fp32 path
+template <typename T>
+static int fwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, float* m, float* l,
+                    cudaStream_t st) {
+  AttnParams p = make_params(a);
+  const int nqt = (p.N + 63) / 64;
+  const int dcap = p.d < 256 ? p.d : 256;
+  const int nch = dcap <= 64 ? 1 : (dcap <= 128 ? 2 : 4);
+  const int nslice = (p.d + nch * 64 - 1) / (nch * 64);
+  dim3 grid(nqt * nslice, p.H, p.B);
+  auto launch = [&](auto kern) -> int {
+    FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32k::kSmemFwd));
+    kern<<<grid, f32k::NT, f32k::kSmemFwd, st>>>(p, (const T*)Q, (const T*)K, (const T*)V, (T*)O, m, l);
+    FA_CUDA_CHECK(cudaGetLastError());
+    return FA_OK;
+  };
+  if (nch == 1) return launch(f32k::fwd_kernel<T, 1>);
+  if (nch == 2) return launch(f32k::fwd_kernel<T, 2>);
+  return launch(f32k::fwd_kernel<T, 4>);
+}
+
+template <typename T>
+static int bwd_prep(const AttnParams& p, const void* O, const void* dO, const float* m, const float* l, float* Dv,
+                    float* LSE, cudaStream_t st) {
+  const long long rows = (long long)p.B * p.H * p.N;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  f32k::bwd_prep_kernel<T><<<(int)blocks, 256, 0, st>>>(p, (const T*)O, (const T*)dO, m, l, Dv, LSE);
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+template <typename T>
+static int bwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                    const float* m, const float* l, void* dQ, void* dK, void* dV, cudaStream_t st) {
+  AttnParams p = make_params(a);
+  const long long rows = (long long)p.B * p.H * p.N;
+  float* ws = static_cast<float*>(g_pool.get(12, sizeof(float) * 2 * rows));
+  if (!ws) return set_error(FA_ERR_CUDA, "flash bwd: workspace allocation failed");
+  float *Dv = ws, *LSE = ws + rows;
+  int rc = bwd_prep<T>(p, O, dO, m, l, Dv, LSE, st);
+  if (rc != FA_OK) return rc;
+  const int nt = (p.N + 63) / 64;
+  {
+    const int dcap = p.d < 128 ? p.d : 128;
+    const int nch = dcap <= 64 ? 1 : 2;
+    const int nslice = (p.d + nch * 64 - 1) / (nch * 64);
+    dim3 grid(nt * nslice, p.H, p.B);
+    auto launch = [&](auto kern) -> int {
+      FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32k::kSmemBwd));
+      kern<<<grid, f32k::NT, f32k::kSmemBwd, st>>>(p, (const T*)Q, (const T*)K, (const T*)V, (const T*)dO, Dv, LSE,
+                                                   (T*)dK, (T*)dV);
+      FA_CUDA_CHECK(cudaGetLastError());
+      return FA_OK;
+    };
+    rc = (nch == 1) ? launch(f32k::bwd_dkdv_kernel<T, 1>) : launch(f32k::bwd_dkdv_kernel<T, 2>);
+    if (rc != FA_OK) return rc;
+  }
+  {
+    const int dcap = p.d < 256 ? p.d : 256;
+    const int nch = dcap <= 64 ? 1 : (dcap <= 128 ? 2 : 4);
+    const int nslice = (p.d + nch * 64 - 1) / (nch * 64);
+    dim3 grid(nt * nslice, p.H, p.B);
+    auto launch = [&](auto kern) -> int {
+      FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32k::kSmemBwd));
+      kern<<<grid, f32k::NT, f32k::kSmemBwd, st>>>(p, (const T*)Q, (const T*)K, (const T*)V, (const T*)dO, Dv, LSE,
+                                                   (T*)dQ);
+      FA_CUDA_CHECK(cudaGetLastError());
+      return FA_OK;
+    };
+    if (nch == 1) return launch(f32k::bwd_dq_kernel<T, 1>);
+    if (nch == 2) return launch(f32k::bwd_dq_kernel<T, 2>);
+    return launch(f32k::bwd_dq_kernel<T, 4>);
+  }
+}
+
+// ------------------------------------------------------------------------------ tensor-core path
+template <int D, bool CAUSAL, int MASKMODE, typename OutT, int PMODE>
+static int launch_fwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const sm100::FwdParams& fp, cudaStream_t st) {
+  using Cfg = sm100::FwdCfg<D, PMODE>;
+  auto kern = sm100::fwd_kernel<D, CAUSAL, MASKMODE, OutT, PMODE>;
+  FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  dim3 grid((a->N + 255) / 256, a->H, a->B);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, fp);
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+// OutT = bf16 for the device API; float when the legacy fp32 ABI wants fp32 O straight from the kernel.
+template <typename OutT>
+static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, long long o_sb,
+                  long long o_sh, long long o_sn, float* m, float* l, cudaStream_t st) {
+  Strides s = resolve_strides(a);
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap(&tq, Q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, a->H, a->N, a->d, s.sb, s.sh, s.sn, 64, 128)))
+    return rc;
+  if ((rc = make_tmap(&tk, K, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, a->H, a->N, a->d, s.sb, s.sh, s.sn, 64, 128)))
+    return rc;
+  if ((rc = make_tmap(&tv, V, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, a->H, a->N, a->d, s.sb, s.sh, s.sn, 64, 128)))
+    return rc;
+  sm100::FwdParams fp;
+  fp.B = a->B, fp.H = a->H, fp.N = a->N;
+  fp.kv_len = a->kv_len;
+  fp.key_mask = a->key_mask;
+  fp.O = O;
+  fp.o_sb = o_sb, fp.o_sh = o_sh, fp.o_sn = o_sn;
+  fp.M = m, fp.L = l;
+  fp.scale = 1.0f / sqrtf((float)a->d);
+  fp.scale_log2 = fp.scale * 1.4426950408889634f;
+  const int maskmode = a->key_mask ? 2 : (a->kv_len ? 1 : 0);
+  current_mode();
+  const int pmode = g_pmode;
+#define FA_FWD_CASE(DD, CC, MM)                                                                   \
+  if (a->d == DD && (a->causal != 0) == CC && maskmode == MM) {                                   \
+    return pmode ? launch_fwd_tc<DD, CC, MM, OutT, 1>(a, tq, tk, tv, fp, st)                      \
+                 : launch_fwd_tc<DD, CC, MM, OutT, 0>(a, tq, tk, tv, fp, st);                     \
+  }
+  FA_FWD_CASE(128, false, 0) FA_FWD_CASE(128, true, 0) FA_FWD_CASE(128, false, 1) FA_FWD_CASE(128, true, 1)
+  FA_FWD_CASE(128, false, 2) FA_FWD_CASE(128, true, 2) FA_FWD_CASE(64, false, 0) FA_FWD_CASE(64, true, 0)
+  FA_FWD_CASE(64, false, 1) FA_FWD_CASE(64, true, 1) FA_FWD_CASE(64, false, 2) FA_FWD_CASE(64, true, 2)
+#undef FA_FWD_CASE
+  return set_error(FA_ERR_UNSUPPORTED, "flash fwd (tensor core): head_dim %d not supported", a->d);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y), o.y = pack_bf16x2(a.z, a.w), o.z = pack_bf16x2(b.x, b.y), o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + i) = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t t = n & ~size_t(7); t < n; ++t) dst[t] = __float2bfloat16_rn(src[t]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t n) {
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = __uint_as_float(w[k] << 16);
+      o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+    *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t t = n & ~size_t(7); t < n; ++t) dst[t] = __bfloat162float(src[t]);
+}
+static int cast_grid(size_t n) {
+  size_t b = (n / 8 + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+void fa_set_mode(int mode) {
+  current_mode();
+  g_mode = (mode == FA_MODE_BF16) ? FA_MODE_BF16 : FA_MODE_FP32;
+}
+int fa_get_mode(void) { return current_mode(); }
+// debug only (not part of the public header): 1 routes P through shared memory instead of TMEM
+void fa_debug_set_pmode(int pmode) {
+  current_mode();
+  g_pmode = pmode ? 1 : 0;
+}
+
+int fa_cast_f32_to_bf16_dev(const float* src, void* dst, size_t n, fa_stream_t stream) {
+  clear_error();
+  if (n == 0) return FA_OK;
+  cast_f32_bf16_kernel<<<cast_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+int fa_cast_bf16_to_f32_dev(const void* src, float* dst, size_t n, fa_stream_t stream) {
+  clear_error();
+  if (n == 0) return FA_OK;
+  cast_bf16_f32_kernel<<<cast_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, n);
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+double fa_attn_flops(int B, int H, int N, int d, int causal, const int* kv_len_host, int backward) {
+  // fwd 4*B*H*Nq*Nk*d, bwd 10*..., causal halves, padding replaces Nk by kv_len[b].
+  double pairs = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const double nk = kv_len_host ? (double)(kv_len_host[b] < N ? kv_len_host[b] : N) : (double)N;
+    // causal: query i sees min(i+1, nk) keys; counted with the usual "x 1/2" convention
+    pairs += causal ? (0.5 * nk * nk + ((double)N - nk) * nk) : (double)N * nk;
+  }
+  return (backward ? 10.0 : 4.0) * (double)H * (double)d * pairs;
+}
+
+int fa_flash_fwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, float* m, float* l,
+                     fa_stream_t stream) {
+  clear_error();
+  int rc = validate(a, "fa_flash_fwd_dev");
+  if (rc) return rc;
+  if (!Q || !K || !V || !O || !m || !l) return set_error(FA_ERR_INVALID, "fa_flash_fwd_dev: null tensor pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == FA_DTYPE_F32) return fwd_simt<float>(a, Q, K, V, O, m, l, st);
+  if (tc_supported(a)) {
+    Strides s = resolve_strides(a);
+    return fwd_tc<__nv_bfloat16>(a, Q, K, V, O, s.sb, s.sh, s.sn, m, l, st);
+  }
+  // bf16 tensors with a head dim the tcgen05 kernels do not tile: CUDA-core kernel, fp32 math
+  return fwd_simt<__nv_bfloat16>(a, Q, K, V, O, m, l, st);
+}
+
+int fa_flash_bwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                     const float* m, const float* l, void* dQ, void* dK, void* dV, fa_stream_t stream) {
+  clear_error();
+  int rc = validate(a, "fa_flash_bwd_dev");
+  if (rc) return rc;
+  if (!Q || !K || !V || !O || !dO || !m || !l || !dQ || !dK || !dV)
+    return set_error(FA_ERR_INVALID, "fa_flash_bwd_dev: null tensor pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == FA_DTYPE_F32) return bwd_simt<float>(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
+  if (tc_supported(a)) {
+    int r2 = sm100::bwd_tc(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
+    if (r2 != FA_ERR_UNSUPPORTED) return r2;
+    clear_error();
+  }
+  return bwd_simt<__nv_bfloat16>(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Legacy host-pointer ABI.  fp32 host buffers in, fp32 host buffers out.
+// ---------------------------------------------------------------------------------------------
+static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, float* m, const float* key_mask,
+                           int causal, int B, int nh, int N, int d) {
+  clear_error();
+  fa_attn_desc a{};
+  a.B = B, a.H = nh, a.N = N, a.d = d, a.causal = causal;
+  a.dtype = FA_DTYPE_F32;
+  if (validate(&a, "launch_flashattention_forward")) return;
+  const size_t n = (size_t)B * nh * N * d, r = (size_t)B * nh * N;
+  float* dQ_ = static_cast<float*>(g_pool.get(0, n * 4));
+  float* dK_ = static_cast<float*>(g_pool.get(1, n * 4));
+  float* dV_ = static_cast<float*>(g_pool.get(2, n * 4));
+  float* dO_ = static_cast<float*>(g_pool.get(3, n * 4));
+  float* dml = static_cast<float*>(g_pool.get(4, 2 * r * 4 + (size_t)B * N * 4));
+  if (!dQ_ || !dK_ || !dV_ || !dO_ || !dml) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed (%zu bytes per tensor)", n * 4);
+    return;
+  }
+  float *dm = dml, *dl = dml + r, *dmask = dml + 2 * r;
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t x) {
+    if (e == cudaSuccess) e = x;
+  };
+  step(cudaMemcpyAsync(dQ_, Q, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(dK_, K, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(dV_, V, n * 4, cudaMemcpyHostToDevice, 0));
+  if (key_mask) {
+    step(cudaMemcpyAsync(dmask, key_mask, (size_t)B * N * 4, cudaMemcpyHostToDevice, 0));
+    a.key_mask = dmask;
+  }
+  if (e != cudaSuccess) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_forward: H2D: %s", cudaGetErrorString(e));
+    return;
+  }
+  int rc;
+  if (current_mode() == FA_MODE_BF16 && (d == 64 || d == 128)) {
+    // round the operands to bf16 on device; the kernel writes fp32 O directly
+    __nv_bfloat16* bq = static_cast<__nv_bfloat16*>(g_pool.get(5, n * 2));
+    __nv_bfloat16* bk = static_cast<__nv_bfloat16*>(g_pool.get(6, n * 2));
+    __nv_bfloat16* bv = static_cast<__nv_bfloat16*>(g_pool.get(7, n * 2));
+    if (!bq || !bk || !bv) {
+      set_error(FA_ERR_CUDA, "launch_flashattention_forward: bf16 staging allocation failed");
+      return;
+    }
+    if (fa_cast_f32_to_bf16_dev(dQ_, bq, n, 0) || fa_cast_f32_to_bf16_dev(dK_, bk, n, 0) ||
+        fa_cast_f32_to_bf16_dev(dV_, bv, n, 0))
+      return;
+    a.dtype = FA_DTYPE_BF16;
+    rc = fwd_tc<float>(&a, bq, bk, bv, dO_, (long long)nh * N * d, (long long)N * d, d, dm, dl, 0);
+  } else {
+    rc = fa_flash_fwd_dev(&a, dQ_, dK_, dV_, dO_, dm, dl, 0);
+  }
+  if (rc != FA_OK) return;
+  step(cudaMemcpyAsync(O, dO_, n * 4, cudaMemcpyDeviceToHost, 0));
+  step(cudaMemcpyAsync(m, dm, r * 4, cudaMemcpyDeviceToHost, 0));
+  step(cudaMemcpyAsync(l, dl, r * 4, cudaMemcpyDeviceToHost, 0));
+  step(cudaStreamSynchronize(0));
+  if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_forward: %s", cudaGetErrorString(e));
+}
+
+// bf16 mode of the legacy backward: round the fp32 operands to bf16 on device, run the bf16
+// backward, widen the gradients back to fp32 in place of the fp32 staging buffers.
+static int bwd_bf16_from_f32(fa_attn_desc* a, float* gQ, float* gK, float* gV, float* gO, float* gdO, const float* dm,
+                             const float* dl, float* gdQ, float* gdK, float* gdV) {
+  const size_t n = (size_t)a->B * a->H * a->N * a->d;
+  __nv_bfloat16* b[8];
+  for (int i = 0; i < 8; ++i) {
+    b[i] = static_cast<__nv_bfloat16*>(g_pool.get(16 + i, n * 2));
+    if (!b[i]) return set_error(FA_ERR_CUDA, "launch_flashattention_backward: bf16 staging allocation failed");
+  }
+  float* src[5] = {gQ, gK, gV, gO, gdO};
+  for (int i = 0; i < 5; ++i)
+    if (int rc = fa_cast_f32_to_bf16_dev(src[i], b[i], n, 0)) return rc;
+  a->dtype = FA_DTYPE_BF16;
+  if (int rc = fa_flash_bwd_dev(a, b[0], b[1], b[2], b[3], b[4], dm, dl, b[5], b[6], b[7], 0)) return rc;
+  float* dst[3] = {gdQ, gdK, gdV};
+  for (int i = 0; i < 3; ++i)
+    if (int rc = fa_cast_bf16_to_f32_dev(b[5 + i], dst[i], n, 0)) return rc;
+  return FA_OK;
+}
+
+static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV, float* dO,
+                            float* l, float* m, const float* key_mask, int causal, int B, int nh, int N, int d) {
+  clear_error();
+  fa_attn_desc a{};
+  a.B = B, a.H = nh, a.N = N, a.d = d, a.causal = causal;
+  a.dtype = FA_DTYPE_F32;
+  if (validate(&a, "launch_flashattention_backward")) return;
+  const size_t n = (size_t)B * nh * N * d, r = (size_t)B * nh * N;
+  float* buf[8];
+  for (int i = 0; i < 8; ++i) {
+    buf[i] = static_cast<float*>(g_pool.get(i, n * 4));
+    if (!buf[i]) {
+      set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed (%zu bytes per tensor)", n * 4);
+      return;
+    }
+  }
+  float* dml = static_cast<float*>(g_pool.get(9, 2 * r * 4 + (size_t)B * N * 4));
+  if (!dml) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed");
+    return;
+  }
+  float *dm = dml, *dl = dml + r, *dmask = dml + 2 * r;
+  float *gQ = buf[0], *gK = buf[1], *gV = buf[2], *gO = buf[3], *gdO = buf[4], *gdQ = buf[5], *gdK = buf[6],
+        *gdV = buf[7];
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t x) {
+    if (e == cudaSuccess) e = x;
+  };
+  step(cudaMemcpyAsync(gQ, Q, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(gK, K, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(gV, V, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(gO, O, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(gdO, dO, n * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(dm, m, r * 4, cudaMemcpyHostToDevice, 0));
+  step(cudaMemcpyAsync(dl, l, r * 4, cudaMemcpyHostToDevice, 0));
+  if (key_mask) {
+    step(cudaMemcpyAsync(dmask, key_mask, (size_t)B * N * 4, cudaMemcpyHostToDevice, 0));
+    a.key_mask = dmask;
+  }
+  if (e != cudaSuccess) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_backward: H2D: %s", cudaGetErrorString(e));
+    return;
+  }
+  int rc;
+  if (current_mode() == FA_MODE_BF16 && (d == 64 || d == 128)) {
+    rc = bwd_bf16_from_f32(&a, gQ, gK, gV, gO, gdO, dm, dl, gdQ, gdK, gdV);
+  } else {
+    rc = fa_flash_bwd_dev(&a, gQ, gK, gV, gO, gdO, dm, dl, gdQ, gdK, gdV, 0);
+  }
+  if (rc != FA_OK) return;
+  step(cudaMemcpyAsync(dQ, gdQ, n * 4, cudaMemcpyDeviceToHost, 0));
+  step(cudaMemcpyAsync(dK, gdK, n * 4, cudaMemcpyDeviceToHost, 0));
+  step(cudaMemcpyAsync(dV, gdV, n * 4, cudaMemcpyDeviceToHost, 0));
+  step(cudaStreamSynchronize(0));
+  if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
+}
+
+void launch_flashattention_forward(float* Q, float* K, float* V, float* O, float* l, float* m, int B, int nh, int N,
+                                   int d) {
+  legacy_forward(Q, K, V, O, l, m, nullptr, 0, B, nh, N, d);
+}
+void launch_flashattention_forward_causal(float* Q, float* K, float* V, float* O, float* l, float* m, int B, int nh,
+                                          int N, int d) {
+  legacy_forward(Q, K, V, O, l, m, nullptr, 1, B, nh, N, d);
+}
+void launch_flashattention_forward_masked(float* Q, float* K, float* V, float* O, float* l, float* m,
+                                          const float* key_mask, int causal, int B, int nh, int N, int d) {
+  legacy_forward(Q, K, V, O, l, m, key_mask, causal ? 1 : 0, B, nh, N, d);
+}
+void launch_flashattention_backward(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV, float* dO,
+                                    float* l, float* m, int B, int nh, int N, int d) {
+  legacy_backward(Q, K, V, O, dQ, dK, dV, dO, l, m, nullptr, 0, B, nh, N, d);
+}
+void launch_flashattention_backward_causal(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV,
+                                           float* dO, float* l, float* m, int B, int nh, int N, int d) {
+  legacy_backward(Q, K, V, O, dQ, dK, dV, dO, l, m, nullptr, 1, B, nh, N, d);
+}
+void launch_flashattention_backward_masked(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV,
+                                           float* dO, float* l, float* m, const float* key_mask, int causal, int B,
+                                           int nh, int N, int d) {
+  legacy_backward(Q, K, V, O, dQ, dK, dV, dO, l, m, key_mask, causal ? 1 : 0, B, nh, N, d);
+}
+
+}  // extern "C"

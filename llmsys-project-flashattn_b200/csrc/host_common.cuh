@@ -1,0 +1,171 @@
+// Host-side plumbing shared by the three shared libraries (included once per .so):
+// status/error reporting, a grow-only device scratch pool for the legacy host-pointer
+// entry points (the reference does cudaMalloc/cudaFree on every call,
+// src/flashattention_kernel.cu:280-324), and the fa_* utility exports declared in
+// include/flashattn_b200.h.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "../../include/flashattn_b200.h"
+
+namespace fa {
+
+static thread_local int g_status = FA_OK;
+static thread_local char g_errmsg[512] = "";
+
+inline int set_error(int code, const char* fmt, ...) {
+  g_status = code;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_errmsg, sizeof(g_errmsg), fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline void clear_error() {
+  g_status = FA_OK;
+  g_errmsg[0] = 0;
+}
+
+#define FA_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return fa::set_error(FA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                           __FILE__, __LINE__);                                                  \
+  } while (0)
+
+// Grow-only scratch slots, one set per device.  Single-threaded callers (ctypes from Python).
+struct ScratchPool {
+  static constexpr int kSlots = 32;
+  static constexpr int kMaxDev = 16;
+  void* ptr[kMaxDev][kSlots] = {};
+  size_t cap[kMaxDev][kSlots] = {};
+  void* get(int slot, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDev || slot < 0 || slot >= kSlots) return nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cap[dev][slot] >= bytes) return ptr[dev][slot];
+    if (ptr[dev][slot]) cudaFree(ptr[dev][slot]);
+    ptr[dev][slot] = nullptr;
+    cap[dev][slot] = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&ptr[dev][slot], want) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    cap[dev][slot] = want;
+    return ptr[dev][slot];
+  }
+};
+static ScratchPool g_pool;
+
+}  // namespace fa
+
+extern "C" {
+int fa_last_status(void) { return fa::g_status; }
+const char* fa_last_error(void) { return fa::g_errmsg; }
+int fa_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int fa_set_device(int dev) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaSetDevice(dev));
+  return FA_OK;
+}
+void* fa_malloc(size_t bytes) {
+  fa::clear_error();
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    fa::set_error(FA_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+void* fa_malloc_host(size_t bytes) {
+  fa::clear_error();
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    fa::set_error(FA_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+int fa_free(void* p) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaFree(p));
+  return FA_OK;
+}
+int fa_free_host(void* p) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaFreeHost(p));
+  return FA_OK;
+}
+int fa_memset(void* p, int byte, size_t bytes) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaMemset(p, byte, bytes));
+  return FA_OK;
+}
+int fa_h2d(void* dst, const void* src, size_t bytes) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return FA_OK;
+}
+int fa_d2h(void* dst, const void* src, size_t bytes) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return FA_OK;
+}
+int fa_sync(void) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaDeviceSynchronize());
+  return FA_OK;
+}
+void* fa_event_create(void) {
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return e;
+}
+int fa_event_record(void* ev, fa_stream_t s) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev), reinterpret_cast<cudaStream_t>(s)));
+  return FA_OK;
+}
+float fa_event_elapsed_ms(void* a, void* b) {
+  fa::clear_error();
+  float ms = -1.f;
+  if (cudaEventSynchronize(static_cast<cudaEvent_t>(b)) != cudaSuccess ||
+      cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)) != cudaSuccess) {
+    fa::set_error(FA_ERR_CUDA, "event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1.f;
+  }
+  return ms;
+}
+int fa_event_destroy(void* ev) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+  return FA_OK;
+}
+int fa_flush_l2(void) {
+  fa::clear_error();
+  const size_t bytes = 256ull << 20;  // > 126 MB L2
+  void* p = fa::g_pool.get(fa::ScratchPool::kSlots - 1, bytes);
+  if (!p) return fa::set_error(FA_ERR_CUDA, "flush buffer allocation failed");
+  FA_CUDA_CHECK(cudaMemsetAsync(p, 1, bytes, 0));
+  return FA_OK;
+}
+}  // extern "C"

@@ -1,0 +1,414 @@
+// layernorm_kernel.so -- LayerNorm forward / backward for sm_100a.
+//
+// Replaces the reference's LightSeq-derived src/layernorm_kernel.cu (ker_layer_norm :37,
+// ker_ln_bw_dgamma_dbetta :193, ker_ln_bw_dinp :292) behind the same C ABI (launch_layernorm
+// :101, launch_layernorm_bw :370).  Both directions are HBM-bound; the design goal is the
+// algorithmic minimum traffic with 128-bit coalesced accesses:
+//   forward : x read once (registers), y written once            -> 8 B/elem
+//   backward: x and dy read once, dx written once; dgamma/dbeta are accumulated in registers
+//             across the rows a CTA owns and reduced through a tiny [grid][h] workspace
+//             -> 12 B/elem (the reference reads x and dy twice: 20 B/elem)
+// Semantics kept from the reference: `vars` stores var + 1e-8 (:70) and the backward adds
+// 1e-8 again (:229, :310); hidden_dim % 4 == 0 is required (:105); the 4096 cap of the
+// backward (:411) is lifted to 16384.
+#include <cstdint>
+
+#include "host_common.cuh"
+
+namespace fa {
+
+constexpr float kLnEps = 1e-8f;  // LN_EPSILON, reference src/layernorm_kernel.cu:12
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum of `v` over the TPR threads that own one row.  TPR == 32: a warp shuffle.  Otherwise the
+// row is owned by the whole CTA (blockDim.x == TPR).
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* red) {
+  v = warp_sum(v);
+  if constexpr (TPR == 32) {
+    return v;
+  } else {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int NW = TPR / 32;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < NW) ? red[lane] : 0.f;
+    return warp_sum(r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward.  BLOCK threads; a row is owned by TPR threads, each holding ITERS float4.
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK, int TPR, int ITERS>
+__global__ void __launch_bounds__(BLOCK) layernorm_fw_kernel(float* __restrict__ y, float* __restrict__ vars,
+                                                             float* __restrict__ means,
+                                                             const float* __restrict__ x,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long rows,
+                                                             int h) {
+  __shared__ float red[32];
+  constexpr int RPC = BLOCK / TPR;
+  const int sub = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  const int h4 = h >> 2;
+  const float inv_h = 1.0f / static_cast<float>(h);
+  for (long long row0 = static_cast<long long>(blockIdx.x) * RPC; row0 < rows;
+       row0 += static_cast<long long>(gridDim.x) * RPC) {
+    const long long row = row0 + sub;
+    const bool ok = row < rows;
+    const long long rr = ok ? row : rows - 1;
+    const float4* xr = reinterpret_cast<const float4*>(x + rr * h);
+    float4 v[ITERS];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * TPR + t;
+      v[it] = (c < h4) ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+    }
+    const float mean = row_sum<TPR>(s, red) * inv_h;
+    float sq = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * TPR + t;
+      if (c < h4) {
+        const float a = v[it].x - mean, b = v[it].y - mean, cc = v[it].z - mean, d = v[it].w - mean;
+        sq += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float var = row_sum<TPR>(sq, red) * inv_h + kLnEps;  // stored WITH eps (reference :70)
+    const float rstd = rsqrtf(var);
+    if (ok) {
+      if (t == 0) {
+        means[row] = mean;
+        vars[row] = var;
+      }
+      float4* yr = reinterpret_cast<float4*>(y + row * h);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = it * TPR + t;
+        if (c < h4) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+          float4 o;
+          o.x = g.x * ((v[it].x - mean) * rstd) + b.x;
+          o.y = g.y * ((v[it].y - mean) * rstd) + b.y;
+          o.z = g.z * ((v[it].z - mean) * rstd) + b.z;
+          o.w = g.w * ((v[it].w - mean) * rstd) + b.w;
+          yr[c] = o;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, fused: dx per row + per-CTA partial dgamma / dbeta.
+//   xhat = (x - mean) / sqrt(var + eps)           (reference :229, :310 -- eps a second time)
+//   dxhat = dy * gamma
+//   dx = (dxhat - (sum(dxhat) + xhat * sum(dxhat*xhat)) / h) / sd      (reference :348-362)
+// part_g / part_b: [gridDim.x][h] fp32 partial sums, reduced by ln_bw_reduce_kernel.
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK, int TPR, int ITERS>
+__global__ void __launch_bounds__(BLOCK) layernorm_bw_kernel(float* __restrict__ dx, float* __restrict__ part_g,
+                                                             float* __restrict__ part_b,
+                                                             const float* __restrict__ dy,
+                                                             const float* __restrict__ x,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ vars,
+                                                             const float* __restrict__ means, long long rows,
+                                                             int h) {
+  extern __shared__ float4 sm_part[];  // RPC > 1: [2][RPC][h4] cross-row-group reduction buffer
+  __shared__ float red[32];
+  constexpr int RPC = BLOCK / TPR;
+  const int sub = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  const int h4 = h >> 2;
+  const float inv_h = 1.0f / static_cast<float>(h);
+
+  float4 g4[ITERS], acc_g[ITERS], acc_b[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int c = it * TPR + t;
+    g4[it] = (c < h4) ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_g[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  for (long long row0 = static_cast<long long>(blockIdx.x) * RPC; row0 < rows;
+       row0 += static_cast<long long>(gridDim.x) * RPC) {
+    const long long row = row0 + sub;
+    const bool ok = row < rows;
+    const long long rr = ok ? row : rows - 1;
+    const float4* xr = reinterpret_cast<const float4*>(x + rr * h);
+    const float4* dyr = reinterpret_cast<const float4*>(dy + rr * h);
+    const float mean = __ldg(means + rr);
+    const float rstd = rsqrtf(__ldg(vars + rr) + kLnEps);
+    float4 xh[ITERS], dxh[ITERS];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * TPR + t;
+      if (c < h4) {
+        const float4 xv = __ldg(xr + c);
+        const float4 dv = __ldg(dyr + c);
+        xh[it] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
+                             (xv.w - mean) * rstd);
+        dxh[it] = make_float4(dv.x * g4[it].x, dv.y * g4[it].y, dv.z * g4[it].z, dv.w * g4[it].w);
+        if (ok) {
+          acc_b[it].x += dv.x, acc_b[it].y += dv.y, acc_b[it].z += dv.z, acc_b[it].w += dv.w;
+          acc_g[it].x += dv.x * xh[it].x, acc_g[it].y += dv.y * xh[it].y;
+          acc_g[it].z += dv.z * xh[it].z, acc_g[it].w += dv.w * xh[it].w;
+        }
+        s1 += (dxh[it].x + dxh[it].y) + (dxh[it].z + dxh[it].w);
+        s2 += (dxh[it].x * xh[it].x + dxh[it].y * xh[it].y) + (dxh[it].z * xh[it].z + dxh[it].w * xh[it].w);
+      } else {
+        xh[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dxh[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    s1 = row_sum<TPR>(s1, red) * inv_h;
+    s2 = row_sum<TPR>(s2, red) * inv_h;
+    if (ok) {
+      float4* dxr = reinterpret_cast<float4*>(dx + row * h);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = it * TPR + t;
+        if (c < h4) {
+          float4 o;
+          o.x = (dxh[it].x - s1 - xh[it].x * s2) * rstd;
+          o.y = (dxh[it].y - s1 - xh[it].y * s2) * rstd;
+          o.z = (dxh[it].z - s1 - xh[it].z * s2) * rstd;
+          o.w = (dxh[it].w - s1 - xh[it].w * s2) * rstd;
+          dxr[c] = o;
+        }
+      }
+    }
+  }
+
+  // fold the RPC row groups of this CTA together, then publish one partial row per CTA
+  float4* pg = reinterpret_cast<float4*>(part_g + static_cast<size_t>(blockIdx.x) * h);
+  float4* pb = reinterpret_cast<float4*>(part_b + static_cast<size_t>(blockIdx.x) * h);
+  if constexpr (RPC == 1) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * TPR + t;
+      if (c < h4) pg[c] = acc_g[it], pb[c] = acc_b[it];
+    }
+  } else {
+    float4* sg = sm_part;                 // [RPC][h4]
+    float4* sb = sm_part + RPC * h4;      // [RPC][h4]
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * TPR + t;
+      if (c < h4) sg[sub * h4 + c] = acc_g[it], sb[sub * h4 + c] = acc_b[it];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < h4; c += BLOCK) {
+      float4 a = sg[c], b = sb[c];
+#pragma unroll
+      for (int r = 1; r < RPC; ++r) {
+        const float4 a2 = sg[r * h4 + c], b2 = sb[r * h4 + c];
+        a.x += a2.x, a.y += a2.y, a.z += a2.z, a.w += a2.w;
+        b.x += b2.x, b.y += b2.y, b.z += b2.z, b.w += b2.w;
+      }
+      pg[c] = a, pb[c] = b;
+    }
+  }
+}
+
+// dgamma[c] = sum_p part_g[p][c]; one thread per column, coalesced along h.
+__global__ void ln_bw_reduce_kernel(float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    const float* __restrict__ part_g, const float* __restrict__ part_b,
+                                    int nparts, int h) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= h) return;
+  float g = 0.f, b = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    g += part_g[static_cast<size_t>(p) * h + c];
+    b += part_b[static_cast<size_t>(p) * h + c];
+  }
+  dgamma[c] = g;
+  dbeta[c] = b;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// (BLOCK, TPR, ITERS) by row length in float4 units.
+template <typename F>
+static bool dispatch_ln(int h4, F&& f) {
+  if (h4 <= 32) return f.template operator()<256, 32, 1>(), true;
+  if (h4 <= 64) return f.template operator()<256, 32, 2>(), true;
+  if (h4 <= 128) return f.template operator()<256, 32, 4>(), true;
+  if (h4 <= 256) return f.template operator()<256, 256, 1>(), true;
+  if (h4 <= 512) return f.template operator()<256, 256, 2>(), true;
+  if (h4 <= 1024) return f.template operator()<256, 256, 4>(), true;
+  if (h4 <= 2048) return f.template operator()<512, 512, 4>(), true;
+  if (h4 <= 4096) return f.template operator()<512, 512, 8>(), true;
+  return false;
+}
+
+}  // namespace fa
+
+extern "C" {
+
+int fa_layernorm_dev(float* ln_res, float* vars, float* means, const float* inp, const float* scale,
+                     const float* bias, long long rows, int hidden_dim, fa_stream_t stream) {
+  fa::clear_error();
+  if (hidden_dim <= 0 || hidden_dim % 4 != 0)  // reference :105 throws "violate hidden_dim % 4 = 0"
+    return fa::set_error(FA_ERR_INVALID, "layernorm: violate hidden_dim %% 4 = 0 (hidden_dim=%d)", hidden_dim);
+  if (rows < 0) return fa::set_error(FA_ERR_INVALID, "layernorm: rows=%lld", rows);
+  if (rows == 0) return FA_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  bool ok = fa::dispatch_ln(hidden_dim / 4, [&]<int BLOCK, int TPR, int ITERS>() {
+    constexpr int RPC = BLOCK / TPR;
+    long long need = (rows + RPC - 1) / RPC;
+    long long cap = static_cast<long long>(fa::num_sms()) * (2048 / BLOCK);
+    int grid = static_cast<int>(need < cap ? need : cap);
+    fa::layernorm_fw_kernel<BLOCK, TPR, ITERS>
+        <<<grid, BLOCK, 0, s>>>(ln_res, vars, means, inp, scale, bias, rows, hidden_dim);
+  });
+  if (!ok) return fa::set_error(FA_ERR_UNSUPPORTED, "layernorm: hidden_dim %d > 16384", hidden_dim);
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, const float* out_grad,
+                        const float* inp, const float* gamma, const float* betta, const float* vars,
+                        const float* means, long long rows, int hidden_dim, fa_stream_t stream) {
+  (void)betta;
+  fa::clear_error();
+  if (hidden_dim <= 0 || hidden_dim % 4 != 0)
+    return fa::set_error(FA_ERR_INVALID, "layernorm_bw: hidden_dim %% 4 != 0 (hidden_dim=%d)", hidden_dim);
+  if (rows < 0) return fa::set_error(FA_ERR_INVALID, "layernorm_bw: rows=%lld", rows);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (rows == 0) {
+    FA_CUDA_CHECK(cudaMemsetAsync(gamma_grad, 0, sizeof(float) * hidden_dim, s));
+    FA_CUDA_CHECK(cudaMemsetAsync(betta_grad, 0, sizeof(float) * hidden_dim, s));
+    return FA_OK;
+  }
+  int status = FA_OK;
+  bool ok = fa::dispatch_ln(hidden_dim / 4, [&]<int BLOCK, int TPR, int ITERS>() {
+    constexpr int RPC = BLOCK / TPR;
+    long long need = (rows + RPC - 1) / RPC;
+    // persistent: ~2 CTAs per SM keeps the partial workspace (grid*h*8 B) small
+    long long cap = static_cast<long long>(fa::num_sms()) * ((BLOCK <= 256) ? 4 : 1);
+    int grid = static_cast<int>(need < cap ? need : cap);
+    float* part = static_cast<float*>(fa::g_pool.get(8, sizeof(float) * 2 * static_cast<size_t>(grid) * hidden_dim));
+    if (!part) {
+      status = fa::set_error(FA_ERR_CUDA, "layernorm_bw: workspace allocation failed");
+      return;
+    }
+    float* part_g = part;
+    float* part_b = part + static_cast<size_t>(grid) * hidden_dim;
+    size_t smem = (RPC > 1) ? sizeof(float) * 2 * RPC * hidden_dim : 0;
+    fa::layernorm_bw_kernel<BLOCK, TPR, ITERS><<<grid, BLOCK, smem, s>>>(inp_grad, part_g, part_b, out_grad, inp,
+                                                                         gamma, vars, means, rows, hidden_dim);
+    fa::ln_bw_reduce_kernel<<<(hidden_dim + 255) / 256, 256, 0, s>>>(gamma_grad, betta_grad, part_g, part_b, grid,
+                                                                     hidden_dim);
+  });
+  if (status != FA_OK) return status;
+  if (!ok) return fa::set_error(FA_ERR_UNSUPPORTED, "layernorm_bw: hidden_dim %d > 16384", hidden_dim);
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+// ---- legacy host-pointer ABI (reference src/layernorm_kernel.cu:101, :370) -------------------
+void launch_layernorm(float* ln_res, float* vars, float* means, const float* inp, const float* scale,
+                      const float* bias, int batch_size, int hidden_dim, fa_stream_t stream) {
+  fa::clear_error();
+  if (hidden_dim <= 0 || hidden_dim % 4 != 0) {
+    fa::set_error(FA_ERR_INVALID, "launch_layernorm: violate hidden_dim %% 4 = 0 (hidden_dim=%d)", hidden_dim);
+    return;
+  }
+  const size_t n = static_cast<size_t>(batch_size) * hidden_dim;
+  if (n == 0) return;
+  float* d_y = static_cast<float*>(fa::g_pool.get(0, n * 4));
+  float* d_x = static_cast<float*>(fa::g_pool.get(1, n * 4));
+  float* d_small = static_cast<float*>(fa::g_pool.get(2, (2 * static_cast<size_t>(batch_size) + 2 * hidden_dim) * 4));
+  if (!d_y || !d_x || !d_small) {
+    fa::set_error(FA_ERR_CUDA, "launch_layernorm: device allocation failed");
+    return;
+  }
+  float* d_var = d_small;
+  float* d_mean = d_small + batch_size;
+  float* d_g = d_mean + batch_size;
+  float* d_b = d_g + hidden_dim;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t r) {
+    if (e == cudaSuccess) e = r;
+  };
+  step(cudaMemcpyAsync(d_x, inp, n * 4, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(d_g, scale, hidden_dim * 4, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(d_b, bias, hidden_dim * 4, cudaMemcpyHostToDevice, s));
+  if (e == cudaSuccess && fa_layernorm_dev(d_y, d_var, d_mean, d_x, d_g, d_b, batch_size, hidden_dim, stream) != FA_OK)
+    return;
+  step(cudaMemcpyAsync(ln_res, d_y, n * 4, cudaMemcpyDeviceToHost, s));
+  step(cudaMemcpyAsync(vars, d_var, static_cast<size_t>(batch_size) * 4, cudaMemcpyDeviceToHost, s));
+  step(cudaMemcpyAsync(means, d_mean, static_cast<size_t>(batch_size) * 4, cudaMemcpyDeviceToHost, s));
+  step(cudaStreamSynchronize(s));
+  if (e != cudaSuccess) fa::set_error(FA_ERR_CUDA, "launch_layernorm: %s", cudaGetErrorString(e));
+}
+
+void launch_layernorm_bw(float* gamma_grad, float* betta_grad, float* inp_grad, const float* out_grad,
+                         const float* inp, const float* gamma, const float* betta, const float* vars,
+                         const float* means, int batch_size, int hidden_dim, fa_stream_t stream_1,
+                         fa_stream_t stream_2) {
+  (void)stream_2;  // the fused kernel needs one stream; the reference used two (:404-417)
+  fa::clear_error();
+  if (hidden_dim <= 0 || hidden_dim % 4 != 0) {
+    fa::set_error(FA_ERR_INVALID, "launch_layernorm_bw: hidden_dim %% 4 != 0 (hidden_dim=%d)", hidden_dim);
+    return;
+  }
+  const size_t n = static_cast<size_t>(batch_size) * hidden_dim;
+  float* d_dx = static_cast<float*>(fa::g_pool.get(0, n * 4));
+  float* d_dy = static_cast<float*>(fa::g_pool.get(1, n * 4));
+  float* d_x = static_cast<float*>(fa::g_pool.get(3, n * 4));
+  float* d_small = static_cast<float*>(fa::g_pool.get(2, (2 * static_cast<size_t>(batch_size) + 4 * hidden_dim) * 4));
+  if (!d_dx || !d_dy || !d_x || !d_small) {
+    fa::set_error(FA_ERR_CUDA, "launch_layernorm_bw: device allocation failed");
+    return;
+  }
+  float* d_var = d_small;
+  float* d_mean = d_small + batch_size;
+  float* d_g = d_mean + batch_size;
+  float* d_b = d_g + hidden_dim;
+  float* d_dg = d_b + hidden_dim;
+  float* d_db = d_dg + hidden_dim;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_1);
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t r) {
+    if (e == cudaSuccess) e = r;
+  };
+  step(cudaMemcpyAsync(d_dy, out_grad, n * 4, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(d_x, inp, n * 4, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(d_g, gamma, hidden_dim * 4, cudaMemcpyHostToDevice, s));
+  if (betta) step(cudaMemcpyAsync(d_b, betta, hidden_dim * 4, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(d_var, vars, static_cast<size_t>(batch_size) * 4, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(d_mean, means, static_cast<size_t>(batch_size) * 4, cudaMemcpyHostToDevice, s));
+  if (e == cudaSuccess && fa_layernorm_bw_dev(d_dg, d_db, d_dx, d_dy, d_x, d_g, d_b, d_var, d_mean, batch_size,
+                                              hidden_dim, stream_1) != FA_OK)
+    return;
+  step(cudaMemcpyAsync(gamma_grad, d_dg, hidden_dim * 4, cudaMemcpyDeviceToHost, s));
+  step(cudaMemcpyAsync(betta_grad, d_db, hidden_dim * 4, cudaMemcpyDeviceToHost, s));
+  step(cudaMemcpyAsync(inp_grad, d_dx, n * 4, cudaMemcpyDeviceToHost, s));
+  step(cudaStreamSynchronize(s));
+  if (e != cudaSuccess) fa::set_error(FA_ERR_CUDA, "launch_layernorm_bw: %s", cudaGetErrorString(e));
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+"""``CudaKernelOps`` -- the operator surface of the reference's minitorch/cuda_kernel_ops.py
+for the fused ops, backed by the B200 libraries.
+
+Same static-method names, argument order and return tuples as the reference
+(minitorch/cuda_kernel_ops.py: attn_softmax_fw :440, attn_softmax_bw :471, layernorm_fw
+:498, layernorm_bw :543, flash_attention_fw :606, flash_attention_bw :677,
+flash_attention_causal_fw :761, flash_attention_causal_bw :811), so
+``TensorBackend(CudaKernelOps)`` (minitorch/tensor_ops.py:97-104) binds them unchanged.
+Differences, all deliberate:
+  * no pycuda / torch imports (the reference only used them to fetch a stream handle);
+  * every operand is made contiguous (the reference forgot O and dO, :745,:749);
+  * a failing launch raises ``FlashAttnError`` instead of exit()/silent return;
+  * optional ``key_mask`` (additive (B,N) padding mask) on the flash entry points.
+The tensors are duck-typed: anything with the minitorch ``Tensor`` protocol
+(``shape``, ``contiguous()``, ``_tensor._storage`` fp32 1-D numpy, ``zeros(shape)``,
+``backend``, ``Tensor.make``) works -- the reference's own ``minitorch.Tensor`` or the
+stand-alone ``HostTensor`` in tensor.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+datatype = np.float32
+
+
+def _storage(t) -> np.ndarray:
+    return t._tensor._storage
+
+
+def _make_like(ref, arr: np.ndarray):
+    """New tensor of ref's class/backend holding `arr` (fp32, C-order)."""
+    arr = np.ascontiguousarray(arr, dtype=datatype)
+    out = type(ref).make(arr.reshape(-1), tuple(arr.shape), backend=ref.backend)
+    if hasattr(out, "requires_grad_"):
+        out.requires_grad_(True)  # the reference creates m with requires_grad=True (:624-628)
+    return out
+
+
+def _mask_ptr(key_mask, B, N):
+    if key_mask is None:
+        return None, None
+    km = np.ascontiguousarray(key_mask.to_numpy() if hasattr(key_mask, "to_numpy") else key_mask, dtype=datatype)
+    km = km.reshape(B, N)
+    return km, km.ctypes.data_as(_lib.c_void_p)
+
+
+class CudaKernelOps:
+    cuda = True
+
+    # ------------------------------------------------------------------ flash attention
+    @staticmethod
+    def _flash_fw(Q, K, V, causal: bool, key_mask=None):
+        lib = _lib.load("flashattention_kernel")
+        B, nh, N, d = Q.shape
+        O = Q.zeros((B, nh, N, d))
+        l = Q.zeros((B, nh, N))
+        m = _make_like(Q, np.full((B, nh, N), -np.inf, dtype=datatype))
+        Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+        keep, kptr = _mask_ptr(key_mask, B, N)
+        if key_mask is None and not causal:
+            lib.launch_flashattention_forward(_storage(Q), _storage(K), _storage(V), _storage(O), _storage(l),
+                                              _storage(m), B, nh, N, d)
+        elif key_mask is None:
+            lib.launch_flashattention_forward_causal(_storage(Q), _storage(K), _storage(V), _storage(O),
+                                                     _storage(l), _storage(m), B, nh, N, d)
+        else:
+            lib.launch_flashattention_forward_masked(_storage(Q), _storage(K), _storage(V), _storage(O),
+                                                     _storage(l), _storage(m), kptr, int(causal), B, nh, N, d)
+        _lib.check(lib)
+        return O, m, l
+
+    @staticmethod
+    def _flash_bw(Q, K, V, O, dO, m, l, causal: bool, key_mask=None):
+        lib = _lib.load("flashattention_kernel")
+        B, nh, N, d = Q.shape
+        dQ, dK, dV = Q.zeros((B, nh, N, d)), Q.zeros((B, nh, N, d)), Q.zeros((B, nh, N, d))
+        Q, K, V, O, dO, m, l = (t.contiguous() for t in (Q, K, V, O, dO, m, l))
+        keep, kptr = _mask_ptr(key_mask, B, N)
+        args = (_storage(Q), _storage(K), _storage(V), _storage(O), _storage(dQ), _storage(dK), _storage(dV),
+                _storage(dO), _storage(l), _storage(m))
+        if key_mask is None and not causal:
+            lib.launch_flashattention_backward(*args, B, nh, N, d)
+        elif key_mask is None:
+            lib.launch_flashattention_backward_causal(*args, B, nh, N, d)
+        else:
+            lib.launch_flashattention_backward_masked(*args, kptr, int(causal), B, nh, N, d)
+        _lib.check(lib)
+        return dQ, dK, dV
+
+    @staticmethod
+    def flash_attention_fw(Q, K, V, key_mask=None):
+        return CudaKernelOps._flash_fw(Q, K, V, False, key_mask)
+
+    @staticmethod
+    def flash_attention_bw(Q, K, V, O, dO, m, l, key_mask=None):
+        return CudaKernelOps._flash_bw(Q, K, V, O, dO, m, l, False, key_mask)
+
+    @staticmethod
+    def flash_attention_causal_fw(Q, K, V, key_mask=None):
+        return CudaKernelOps._flash_fw(Q, K, V, True, key_mask)
+
+    @staticmethod
+    def flash_attention_causal_bw(Q, K, V, O, dO, m, l, key_mask=None):
+        return CudaKernelOps._flash_bw(Q, K, V, O, dO, m, l, True, key_mask)
+
+    # ------------------------------------------------------------------ fused softmax
+    @staticmethod
+    def attn_softmax_fw(inp, mask, mask_future: bool = False):
+        """In place, like the reference (:440-468): returns `inp` itself."""
+        lib = _lib.load("softmax_kernel")
+        batch_size, nhead, from_len, to_len = inp.shape
+        mptr = None
+        if mask is not None:
+            ms = _storage(mask.contiguous())
+            if ms.size < batch_size * to_len:  # e.g. a (1,1,T,T) dummy: broadcast the first row
+                ms = np.ascontiguousarray(np.broadcast_to(ms[:to_len], (batch_size, to_len))).reshape(-1)
+            mptr = ms.ctypes.data_as(_lib.c_void_p)
+        lib.launch_attn_softmax(_storage(inp), mptr, batch_size, nhead, from_len, to_len, bool(mask_future), None)
+        _lib.check(lib)
+        return inp
+
+    @staticmethod
+    def attn_softmax_bw(out_grad, soft_inp):
+        lib = _lib.load("softmax_kernel")
+        rows = out_grad.shape[0] * out_grad.shape[1] * out_grad.shape[2]
+        softmax_len = soft_inp.shape[3]
+        lib.launch_attn_softmax_bw(_storage(out_grad), _storage(soft_inp), rows, softmax_len, None)
+        _lib.check(lib)
+        return out_grad, soft_inp
+
+    # ------------------------------------------------------------------ fused layernorm
+    @staticmethod
+    def layernorm_fw(inp, gamma, beta):
+        lib = _lib.load("layernorm_kernel")
+        batch_size, hidden_dim = inp.shape
+        ln_res = inp.zeros(inp.shape)
+        var = inp.zeros((batch_size,))
+        means = inp.zeros((batch_size,))
+        inp, gamma, beta = inp.contiguous(), gamma.contiguous(), beta.contiguous()
+        lib.launch_layernorm(_storage(ln_res), _storage(var), _storage(means), _storage(inp), _storage(gamma),
+                             _storage(beta), batch_size, hidden_dim, None)
+        _lib.check(lib)
+        return ln_res, var, means
+
+    @staticmethod
+    def layernorm_bw(out_grad, inp, gamma, beta, var, mean):
+        lib = _lib.load("layernorm_kernel")
+        batch_size, hidden_dim = inp.shape
+        gamma_grad = gamma.zeros((1, gamma.shape[0]))
+        beta_grad = beta.zeros((1, beta.shape[0]))
+        inp_grad = inp.zeros(inp.shape)
+        out_grad, inp, gamma, beta, var, mean = (t.contiguous() for t in (out_grad, inp, gamma, beta, var, mean))
+        lib.launch_layernorm_bw(_storage(gamma_grad), _storage(beta_grad), _storage(inp_grad), _storage(out_grad),
+                                _storage(inp), _storage(gamma), _storage(beta), _storage(var), _storage(mean),
+                                batch_size, hidden_dim, None, None)
+        _lib.check(lib)
+        return inp_grad, gamma_grad, beta_grad
+
+    # ------------------------------------------------------------------ mode switch
+    @staticmethod
+    def set_flash_mode(mode: str) -> None:
+        """'fp32' (default, <=1e-5) or 'bf16' (tcgen05 tensor cores, <=2e-2)."""
+        lib = _lib.load("flashattention_kernel")
+        lib.fa_set_mode({"fp32": _lib.FA_MODE_FP32, "bf16": _lib.FA_MODE_BF16}[mode])
+
+    @staticmethod
+    def get_flash_mode() -> str:
+        lib = _lib.load("flashattention_kernel")
+        return "bf16" if lib.fa_get_mode() == _lib.FA_MODE_BF16 else "fp32"

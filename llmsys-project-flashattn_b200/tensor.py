@@ -1,0 +1,281 @@
+"""Stand-alone host tensor + the four fused autograd Functions of the reference.
+
+The reference's minitorch package cannot travel with this repo, so the parity tests and
+the benchmark need a minimal carrier that speaks the same protocol ``CudaKernelOps``
+expects from ``minitorch.Tensor`` (minitorch/tensor.py:72-436): host fp32 storage behind
+``_tensor._storage`` with shape/strides, ``contiguous``/``permute``/``view``/``zeros``,
+``Tensor.make`` and a ``backend`` whose attributes are the fused ops
+(minitorch/tensor_ops.py:97-104).  The autograd nodes mirror
+minitorch/tensor_functions.py:435-516 (Attn_Softmax, LayerNorm, FlashAttention,
+FlashAttentionCausal) with the Attn_Softmax.backward unpacking bug fixed
+(SURVEY.md 2.4).  Layout ops here are pure index bookkeeping on host memory; all
+arithmetic goes through the CUDA libraries.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from .cuda_kernel_ops import CudaKernelOps
+
+datatype = np.float32
+
+
+class TensorBackend:
+    """Binder with the reference's attribute names (minitorch/tensor_ops.py:97-104)."""
+
+    def __init__(self, ops=CudaKernelOps):
+        self.ops = ops
+        self.cuda = getattr(ops, "cuda", False)
+        for name in ("attn_softmax_fw", "attn_softmax_bw", "layernorm_fw", "layernorm_bw", "flash_attention_fw",
+                     "flash_attention_bw", "flash_attention_causal_fw", "flash_attention_causal_bw"):
+            setattr(self, name, getattr(ops, name))
+
+
+class _Data:
+    """Strided view over a flat fp32 array (the slice of minitorch.TensorData the ops touch)."""
+
+    def __init__(self, storage: np.ndarray, shape: Sequence[int], strides: Optional[Sequence[int]] = None):
+        self._storage = storage
+        self.shape = tuple(int(s) for s in shape)
+        if strides is None:
+            st, acc = [], 1
+            for s in reversed(self.shape):
+                st.append(acc)
+                acc *= s
+            strides = tuple(reversed(st))
+        self.strides = tuple(int(s) for s in strides)
+
+    def is_contiguous(self) -> bool:
+        exp = 1
+        for s, st in zip(reversed(self.shape), reversed(self.strides)):
+            if s != 1 and st != exp:
+                return False
+            exp *= s
+        return True
+
+    def view_array(self) -> np.ndarray:
+        return np.lib.stride_tricks.as_strided(self._storage, self.shape, tuple(s * 4 for s in self.strides))
+
+
+class Context:
+    def __init__(self):
+        self.saved_values: Tuple = ()
+
+    def save_for_backward(self, *values):
+        self.saved_values = values
+
+
+class Function:
+    @classmethod
+    def apply(cls, *inputs: "HostTensor") -> "HostTensor":
+        ctx = Context()
+        out = cls.forward(ctx, *[t.detach() for t in inputs])
+        if any(t.requires_grad() for t in inputs):
+            out._node = (cls, ctx, inputs)
+        return out
+
+
+class HostTensor:
+    def __init__(self, data: _Data, backend: Optional[TensorBackend] = None):
+        self._tensor = data
+        self.backend = backend if backend is not None else default_backend()
+        self.f = self.backend
+        self.grad: Optional[HostTensor] = None
+        self._requires_grad = False
+        self._node = None
+
+    # ---- construction -------------------------------------------------------------
+    @staticmethod
+    def make(storage, shape, strides=None, backend=None) -> "HostTensor":
+        st = np.ascontiguousarray(storage, dtype=datatype).reshape(-1)
+        return HostTensor(_Data(st, shape, strides), backend)
+
+    def zeros(self, shape=None) -> "HostTensor":
+        shape = self.shape if shape is None else tuple(shape)
+        return HostTensor.make(np.zeros(int(np.prod(shape)), dtype=datatype), shape, backend=self.backend)
+
+    def detach(self) -> "HostTensor":
+        return HostTensor(self._tensor, self.backend)
+
+    def requires_grad_(self, x: bool = True) -> None:
+        self._requires_grad = bool(x)
+
+    def requires_grad(self) -> bool:
+        return self._requires_grad or self._node is not None
+
+    # ---- layout -------------------------------------------------------------------
+    @property
+    def shape(self):
+        return self._tensor.shape
+
+    def contiguous(self) -> "HostTensor":
+        if self._tensor.is_contiguous():
+            return self
+        arr = np.ascontiguousarray(self._tensor.view_array())
+        out = HostTensor.make(arr.reshape(-1), self.shape, backend=self.backend)
+        if self.requires_grad():
+            out._node = (_Contiguous, None, (self,))
+        return out
+
+    def permute(self, *order) -> "HostTensor":
+        d = self._tensor
+        out = HostTensor(_Data(d._storage, [d.shape[i] for i in order], [d.strides[i] for i in order]), self.backend)
+        if self.requires_grad():
+            out._node = (_Permute, tuple(order), (self,))
+        return out
+
+    def view(self, *shape) -> "HostTensor":
+        assert self._tensor.is_contiguous(), "view needs a contiguous tensor (minitorch/tensor_functions.py View)"
+        out = HostTensor(_Data(self._tensor._storage, shape), self.backend)
+        if self.requires_grad():
+            out._node = (_View, self.shape, (self,))
+        return out
+
+    def to_numpy(self) -> np.ndarray:
+        return np.array(self._tensor.view_array(), dtype=datatype)
+
+    # ---- fused ops (minitorch/tensor.py:424-436) ------------------------------------
+    def attn_softmax(self, mask: "HostTensor") -> "HostTensor":
+        return Attn_Softmax.apply(self, mask)
+
+    def layernorm(self, gamma: "HostTensor", beta: "HostTensor") -> "HostTensor":
+        return LayerNorm.apply(self, gamma, beta)
+
+    def flash_attention(self, k: "HostTensor", v: "HostTensor") -> "HostTensor":
+        return FlashAttention.apply(self, k, v)
+
+    def flash_attention_causal(self, k: "HostTensor", v: "HostTensor") -> "HostTensor":
+        return FlashAttentionCausal.apply(self, k, v)
+
+    # ---- autodiff -----------------------------------------------------------------
+    def backward(self, grad_output: "HostTensor") -> None:
+        """Reverse-mode sweep over the recorded nodes (minitorch/autodiff.py:130-163)."""
+        order, seen = [], set()
+
+        def visit(t):
+            if id(t) in seen:
+                return
+            seen.add(id(t))
+            if t._node is not None:
+                for inp in t._node[2]:
+                    visit(inp)
+            order.append(t)
+
+        visit(self)
+        grads = {id(self): grad_output}
+        for t in reversed(order):
+            g = grads.pop(id(t), None)
+            if g is None:
+                continue
+            if t._node is None:
+                if t._requires_grad:
+                    t.grad = g if t.grad is None else _add(t.grad, g)
+                continue
+            fn, ctx, inputs = t._node
+            outs = fn.backward(ctx, g)
+            if not isinstance(outs, tuple):
+                outs = (outs,)
+            for inp, gi in zip(inputs, outs):
+                if gi is None or not inp.requires_grad():
+                    continue
+                grads[id(inp)] = gi if id(inp) not in grads else _add(grads[id(inp)], gi)
+
+
+def _add(a: HostTensor, b: HostTensor) -> HostTensor:
+    return tensor_from_numpy(a.to_numpy() + b.to_numpy(), backend=a.backend)
+
+
+class _Contiguous:
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _Permute:
+    @staticmethod
+    def backward(order, g):
+        inv = [0] * len(order)
+        for i, o in enumerate(order):
+            inv[o] = i
+        return g.permute(*inv)
+
+
+class _View:
+    @staticmethod
+    def backward(orig_shape, g):
+        return g.contiguous().view(*orig_shape)
+
+
+class Attn_Softmax(Function):
+    @staticmethod
+    def forward(ctx, inp, mask):
+        out = inp.f.attn_softmax_fw(inp, mask)
+        ctx.save_for_backward(out, mask)   # the softmax OUTPUT is what the backward needs
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        soft, _mask = ctx.saved_values
+        g = tensor_from_numpy(out_grad.to_numpy(), backend=out_grad.backend)  # bw kernel is in place
+        g, _ = out_grad.f.attn_softmax_bw(g, soft)
+        return g, None
+
+
+class LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, inp, gamma, beta):
+        ln_res, var, means = inp.f.layernorm_fw(inp, gamma, beta)
+        ctx.save_for_backward(inp, gamma, beta, var, means)
+        return ln_res
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        inp, gamma, beta, var, means = ctx.saved_values
+        dx, dg, db = out_grad.f.layernorm_bw(out_grad, inp, gamma, beta, var, means)
+        return dx, dg.view(gamma.shape[0]), db.view(beta.shape[0])
+
+
+class FlashAttention(Function):
+    @staticmethod
+    def forward(ctx, Q, K, V):
+        O, m, l = Q.f.flash_attention_fw(Q, K, V)
+        ctx.save_for_backward(Q, K, V, O, m, l)
+        return O
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        Q, K, V, O, m, l = ctx.saved_values
+        return out_grad.f.flash_attention_bw(Q, K, V, O, out_grad, m, l)
+
+
+class FlashAttentionCausal(Function):
+    @staticmethod
+    def forward(ctx, Q, K, V):
+        O, m, l = Q.f.flash_attention_causal_fw(Q, K, V)
+        ctx.save_for_backward(Q, K, V, O, m, l)
+        return O
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        Q, K, V, O, m, l = ctx.saved_values
+        return out_grad.f.flash_attention_causal_bw(Q, K, V, O, out_grad, m, l)
+
+
+_default_backend = None
+
+
+def default_backend() -> TensorBackend:
+    global _default_backend
+    if _default_backend is None:
+        _default_backend = TensorBackend(CudaKernelOps)
+    return _default_backend
+
+
+def tensor_from_numpy(arr, backend: Optional[TensorBackend] = None, requires_grad: bool = False) -> HostTensor:
+    """Same name/meaning as minitorch/tensor_functions.py:632."""
+    arr = np.ascontiguousarray(arr, dtype=datatype)
+    t = HostTensor.make(arr.reshape(-1).copy(), arr.shape, backend=backend)
+    t.requires_grad_(requires_grad)
+    return t

@@ -1,0 +1,90 @@
+"""Our softmax / layernorm kernels against the REFERENCE's own CUDA kernels, compiled from
+/root/reference/src/{softmax,layernorm}_kernel.cu by oracle/build_ref.sh into oracle/_ref/
+(checker libraries; the product never loads them).  Same host inputs through the same legacy
+C ABI on both sides."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import flashattn_b200 as fb
+from tests.gpu_util import maxabs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, ndim=1, flags="C_CONTIGUOUS")
+
+
+def _ref(name):
+    path = os.path.join(REF_DIR, f"ref_{name}.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return ctypes.CDLL(path)
+
+
+@pytest.mark.parametrize("B,H,F,T", [(2, 8, 13, 24), (3, 8, 40, 64), (2, 8, 33, 100), (1, 8, 64, 512),
+                                     (2, 4, 16, 1000)])
+def test_softmax_fw_matches_reference_kernel(B, H, F, T):
+    ref = _ref("softmax_kernel")
+    ref.launch_attn_softmax.argtypes = [_f32, _f32] + [ctypes.c_int] * 4 + [ctypes.c_bool, ctypes.c_void_p]
+    ref.launch_attn_softmax.restype = None
+    mine = fb._lib.load("softmax_kernel")
+    rng = np.random.default_rng(T)
+    x = rng.uniform(-1, 1, B * H * F * T).astype(np.float32)
+    valid = rng.integers(1, T + 1, B)
+    mask = np.where(np.arange(T)[None, :] < valid[:, None], 0.0, -1e8).astype(np.float32).reshape(-1)
+    a, b = x.copy(), x.copy()
+    ref.launch_attn_softmax(a, mask, B, H, F, T, False, None)
+    mine.launch_attn_softmax(b, mask.ctypes.data_as(ctypes.c_void_p), B, H, F, T, False, None)
+    fb._lib.check(mine)
+    assert maxabs(a, b) < 1e-6
+
+
+@pytest.mark.parametrize("rows,T", [(64, 24), (128, 100), (32, 512), (8, 2048)])
+def test_softmax_bw_matches_reference_kernel(rows, T):
+    ref = _ref("softmax_kernel")
+    ref.launch_attn_softmax_bw.argtypes = [_f32, _f32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    ref.launch_attn_softmax_bw.restype = None
+    mine = fb._lib.load("softmax_kernel")
+    rng = np.random.default_rng(rows + T)
+    y = rng.uniform(0, 1, (rows, T)).astype(np.float32)
+    y = (y / y.sum(-1, keepdims=True)).reshape(-1)
+    dy = rng.uniform(-1, 1, rows * T).astype(np.float32)
+    a, b = dy.copy(), dy.copy()
+    ref.launch_attn_softmax_bw(a, y.copy(), rows, T, None)
+    mine.launch_attn_softmax_bw(b, y.copy(), rows, T, None)
+    fb._lib.check(mine)
+    assert maxabs(a, b) < 1e-6
+
+
+@pytest.mark.parametrize("rows,h", [(1024, 32), (77, 256), (33, 1024), (16, 4096)])
+def test_layernorm_matches_reference_kernel(rows, h):
+    ref = _ref("layernorm_kernel")
+    ref.launch_layernorm.argtypes = [_f32] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    ref.launch_layernorm.restype = None
+    ref.launch_layernorm_bw.argtypes = [_f32] * 9 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    ref.launch_layernorm_bw.restype = None
+    mine = fb._lib.load("layernorm_kernel")
+    rng = np.random.default_rng(rows + h)
+    x = rng.uniform(-1, 1, rows * h).astype(np.float32)
+    g = rng.uniform(-1, 1, h).astype(np.float32)
+    be = rng.uniform(-1, 1, h).astype(np.float32)
+    dy = rng.uniform(-1, 1, rows * h).astype(np.float32)
+
+    def run(lib):
+        y, var, mean = np.zeros(rows * h, np.float32), np.zeros(rows, np.float32), np.zeros(rows, np.float32)
+        lib.launch_layernorm(y, var, mean, x, g, be, rows, h, None)
+        dg, db, dx = np.zeros(h, np.float32), np.zeros(h, np.float32), np.zeros(rows * h, np.float32)
+        lib.launch_layernorm_bw(dg, db, dx, dy, x, g, be, var, mean, rows, h, None, None)
+        return y, var, mean, dg, db, dx
+
+    r = run(ref)
+    m = run(mine)
+    fb._lib.check(mine)
+    names = ("y", "var", "mean", "dgamma", "dbeta", "dx")
+    # reference tolerances: kernel_tests/test_layernorm_fw.py:22, test_layernorm_bw.py:22 -- we hold far tighter
+    tol = {"y": 2e-5, "var": 1e-6, "mean": 1e-6, "dgamma": 1e-3, "dbeta": 1e-3, "dx": 2e-4}
+    for n, a, b in zip(names, r, m):
+        assert maxabs(a, b) < tol[n], n
