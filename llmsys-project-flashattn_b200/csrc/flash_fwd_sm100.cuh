@@ -7,7 +7,8 @@
 //   warp  8   : TMA producer (Q tiles once; K,V tiles through an NSTAGE ring)
 //   warp  9   : tcgen05.mma issuer (one lane) + TMEM allocation
 //   warps 10-11: idle (they complete the third warpgroup so setmaxnreg can move its registers
-//               to the softmax groups: 208 regs/thread there, 96 here)
+//               to the softmax groups: 208 regs/thread there, 88 here; the total must stay
+//               within the 168 x 384 registers the CTA was launched with)
 // TMEM (512 columns): S0 | S1 (128 fp32 columns each), O0 | O1 (D columns each).  P (bf16)
 // overwrites the first 64 columns of its S tile and is consumed directly from TMEM as the
 // A operand of the PV MMA, so P never touches shared memory.
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(384, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8) {
-   reg_dealloc<96>();
+   reg_dealloc<88>();
    if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {

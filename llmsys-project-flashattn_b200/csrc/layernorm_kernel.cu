@@ -273,6 +273,9 @@ int fa_layernorm_dev(float* ln_res, float* vars, float* means, const float* inp,
     return fa::set_error(FA_ERR_INVALID, "layernorm: violate hidden_dim %% 4 = 0 (hidden_dim=%d)", hidden_dim);
   if (rows < 0) return fa::set_error(FA_ERR_INVALID, "layernorm: rows=%lld", rows);
   if (rows == 0) return FA_OK;
+  if ((reinterpret_cast<uintptr_t>(ln_res) | reinterpret_cast<uintptr_t>(inp) | reinterpret_cast<uintptr_t>(scale) |
+       reinterpret_cast<uintptr_t>(bias)) & 15)
+    return fa::set_error(FA_ERR_INVALID, "layernorm: tensors must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   bool ok = fa::dispatch_ln(hidden_dim / 4, [&]<int BLOCK, int TPR, int ITERS>() {
     constexpr int RPC = BLOCK / TPR;
@@ -295,6 +298,9 @@ int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, c
   if (hidden_dim <= 0 || hidden_dim % 4 != 0)
     return fa::set_error(FA_ERR_INVALID, "layernorm_bw: hidden_dim %% 4 != 0 (hidden_dim=%d)", hidden_dim);
   if (rows < 0) return fa::set_error(FA_ERR_INVALID, "layernorm_bw: rows=%lld", rows);
+  if ((reinterpret_cast<uintptr_t>(inp_grad) | reinterpret_cast<uintptr_t>(out_grad) |
+       reinterpret_cast<uintptr_t>(inp) | reinterpret_cast<uintptr_t>(gamma)) & 15)
+    return fa::set_error(FA_ERR_INVALID, "layernorm_bw: tensors must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (rows == 0) {
     FA_CUDA_CHECK(cudaMemsetAsync(gamma_grad, 0, sizeof(float) * hidden_dim, s));
@@ -339,14 +345,15 @@ void launch_layernorm(float* ln_res, float* vars, float* means, const float* inp
   if (n == 0) return;
   float* d_y = static_cast<float*>(fa::g_pool.get(0, n * 4));
   float* d_x = static_cast<float*>(fa::g_pool.get(1, n * 4));
-  float* d_small = static_cast<float*>(fa::g_pool.get(2, (2 * static_cast<size_t>(batch_size) + 2 * hidden_dim) * 4));
+  const size_t bpad = (static_cast<size_t>(batch_size) + 3) & ~size_t(3);  // keep gamma/beta 16-byte aligned
+  float* d_small = static_cast<float*>(fa::g_pool.get(2, (2 * bpad + 2 * hidden_dim) * 4));
   if (!d_y || !d_x || !d_small) {
     fa::set_error(FA_ERR_CUDA, "launch_layernorm: device allocation failed");
     return;
   }
   float* d_var = d_small;
-  float* d_mean = d_small + batch_size;
-  float* d_g = d_mean + batch_size;
+  float* d_mean = d_small + bpad;
+  float* d_g = d_mean + bpad;
   float* d_b = d_g + hidden_dim;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
@@ -379,14 +386,15 @@ void launch_layernorm_bw(float* gamma_grad, float* betta_grad, float* inp_grad, 
   float* d_dx = static_cast<float*>(fa::g_pool.get(0, n * 4));
   float* d_dy = static_cast<float*>(fa::g_pool.get(1, n * 4));
   float* d_x = static_cast<float*>(fa::g_pool.get(3, n * 4));
-  float* d_small = static_cast<float*>(fa::g_pool.get(2, (2 * static_cast<size_t>(batch_size) + 4 * hidden_dim) * 4));
+  const size_t bpad = (static_cast<size_t>(batch_size) + 3) & ~size_t(3);  // keep gamma/beta 16-byte aligned
+  float* d_small = static_cast<float*>(fa::g_pool.get(2, (2 * bpad + 4 * hidden_dim) * 4));
   if (!d_dx || !d_dy || !d_x || !d_small) {
     fa::set_error(FA_ERR_CUDA, "launch_layernorm_bw: device allocation failed");
     return;
   }
   float* d_var = d_small;
-  float* d_mean = d_small + batch_size;
-  float* d_g = d_mean + batch_size;
+  float* d_mean = d_small + bpad;
+  float* d_g = d_mean + bpad;
   float* d_b = d_g + hidden_dim;
   float* d_dg = d_b + hidden_dim;
   float* d_db = d_dg + hidden_dim;
