@@ -48,6 +48,7 @@ int fa_event_record(void* ev, fa_stream_t s);
 float fa_event_elapsed_ms(void* ev_start, void* ev_stop); /* synchronises on ev_stop */
 int fa_event_destroy(void* ev);
 int fa_flush_l2(void);                         /* overwrite a >L2-sized scratch buffer */
+unsigned long long fa_launch_count(void);      /* kernels launched by this library so far */
 
 /* =====================================================================================
  * flashattention_kernel.so

@@ -56,6 +56,7 @@ _COMMON = {
     "fa_event_elapsed_ms": (c_float, [c_void_p, c_void_p]),
     "fa_event_destroy": (c_int, [c_void_p]),
     "fa_flush_l2": (c_int, []),
+    "fa_launch_count": (ctypes.c_ulonglong, []),
 }
 _HOST4 = [_f32] * 6 + [c_int] * 4
 _HOST4B = [_f32] * 10 + [c_int] * 4

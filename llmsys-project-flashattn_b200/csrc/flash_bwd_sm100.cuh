@@ -1,14 +1,447 @@
-// Flash-attention backward for sm_100a (tcgen05 + TMEM).  Placeholder until the tensor-core
-// backward lands: reports FA_ERR_UNSUPPORTED so the caller uses the CUDA-core backward.
+// Flash-attention backward for sm_100a: recompute-based dQ / dK / dV on tcgen05 + TMEM.
+//
+// One CTA owns one 128-key KV tile of one (batch, head) and sweeps the Q tiles that see it
+// (all of them, or only those at / below the diagonal when causal).  K and V stay resident in
+// shared memory, the dK and dV accumulators stay resident in TMEM for the whole sweep; per
+// Q tile i five tensor-core GEMMs run (all 128x128x128 at d=128):
+//     S^T  = K Q_i^T            (SS)  -> TMEM T_S          scores, transposed: lane = key
+//     dP^T = V dO_i^T           (SS)  -> TMEM T_dP
+//     dV  += P^T dO_i           (TS: P^T is read straight from TMEM, bf16 over T_S)
+//     dQ_i = dS K               (SS)  -> TMEM T_dP (reuses the dP columns once dP is consumed)
+//     dK  += dS^T Q_i           (SS)
+// TMEM: T_S 128 | T_dP/dQ 128 | dV D | dK D columns = 512 at D = 128.
+// Working transposed (lane = key) lets P^T feed the dV GEMM from TMEM and puts dS^T into shared
+// memory in ONE layout that serves both remaining GEMMs: K-major A for dK, MN-major A for dQ.
+// Row statistics LSE_i and D_i = rowsum(dO*O) come from a pre-pass (log2 domain, padded so
+// out-of-range queries get P = 0) and arrive per Q tile with the same TMA transaction.
+//   warps 0-3 / 4-7 : two compute groups that alternate Q tiles (ping-pong): exp2 -> P^T,
+//                     dS^T = P^T*(dP^T - D), then drain dQ_i from TMEM into the fp32 dQ
+//                     accumulator in global memory with red.global.add.v4.f32
+//   warp 8          : TMA producer (K,V once; Q_i, dO_i, LSE_i, D_i through a 2-stage ring)
+//   warp 9          : tcgen05.mma issuer + TMEM allocation
+// The tensor pipe executes in issue order, so single-buffered T_S / T_dP are enough: S^T(i+1)
+// is issued right after dV(i) and overlaps the other group's dS phase.
+// dQ is accumulated across KV-tile CTAs in fp32 (atomic adds; summation order varies between
+// runs) and converted to bf16 * scale by a small kernel afterwards.
 #pragma once
 #include "ptx.cuh"
 
 namespace fa {
 namespace sm100 {
 
-inline int bwd_tc(const fa_attn_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
-                  const float*, void*, void*, void*, cudaStream_t) {
-  return FA_ERR_UNSUPPORTED;
+struct BwdParams {
+  int B, H, N, Npad;
+  const int* kv_len;
+  const float* lse2;   // (B*H, Npad) log2-domain LSE; +inf for rows >= N
+  const float* dvec;   // (B*H, Npad) D_i; 0 for rows >= N
+  float* dq_acc;       // (B,H,N,D) fp32, zero-initialised
+  void* dK;            // bf16 outputs with the strides below
+  void* dV;
+  long long sb, sh, sn;
+  float scale, scale_log2;
+};
+
+template <int D>
+struct BwdCfg {
+  static constexpr int NCHUNK = D / 64;
+  static constexpr int CHUNK_BYTES = 128 * 128;
+  static constexpr int TILE_BYTES = NCHUNK * CHUNK_BYTES;   // K, V, Q_i, dO_i tiles: [128][D] bf16
+  static constexpr int DS_BYTES = 2 * CHUNK_BYTES;          // dS^T tile: [128 keys][128 queries] bf16
+  static constexpr int VEC_BYTES = 2 * 2 * 512;             // [stage][lse2 | D][128] fp32
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = TILE_BYTES;
+  static constexpr int OFF_Q = 2 * TILE_BYTES;              // [2 stages]
+  static constexpr int OFF_DO = 4 * TILE_BYTES;             // [2 stages]
+  static constexpr int OFF_DS = 6 * TILE_BYTES;
+  static constexpr int OFF_VEC = OFF_DS + DS_BYTES;
+  static constexpr int OFF_BAR = OFF_VEC + VEC_BYTES;
+  static constexpr int SMEM_USED = OFF_BAR + 256;
+  static constexpr int SMEM_BYTES = (SMEM_USED + 1024 <= 232448) ? SMEM_USED + 1024 : 232448;
+  static constexpr int T_S = 0, T_DP = 128, T_DV = 256, T_DK = 256 + D;
+  static constexpr int NTHREADS = 384;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* gptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// D_i = sum_x dO*O and LSE_i (log2 domain) for the tensor-core backward; one warp per row,
+// rows padded to Npad per (b,h) with +inf / 0 so that out-of-range queries contribute P = 0.
+__global__ void bwd_prep_tc_kernel(int B, int H, int N, int Npad, int D, long long sb, long long sh, long long sn,
+                                   const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                                   const float* __restrict__ M, const float* __restrict__ L,
+                                   float* __restrict__ lse2, float* __restrict__ dvec) {
+  const long long rows = static_cast<long long>(B) * H * Npad;
+  const int lane = threadIdx.x & 31;
+  for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
+    const int n = static_cast<int>(r % Npad);
+    const long long bh = r / Npad;
+    if (n >= N) {
+      if (lane == 0) {
+        lse2[r] = INFINITY;
+        dvec[r] = 0.f;
+      }
+      continue;
+    }
+    const long long off = (bh / H) * sb + (bh % H) * sh + static_cast<long long>(n) * sn;
+    float s = 0.f;
+    for (int x = lane * 2; x < D; x += 64) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(O + off + x);
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dO + off + x);
+      s += __bfloat162float(a.x) * __bfloat162float(b.x) + __bfloat162float(a.y) * __bfloat162float(b.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const long long sr = bh * N + n;
+      const float l = L[sr];
+      lse2[r] = (l > 0.f) ? (M[sr] + logf(l)) * 1.4426950408889634f : INFINITY;
+      dvec[r] = s;
+    }
+  }
+}
+
+// dQ (bf16) = scale * dq_acc (fp32), contiguous accumulator -> strided output
+__global__ void bwd_convert_dq_kernel(int H, int N, int D, long long sb, long long sh, long long sn, float scale,
+                                      const float* __restrict__ acc, __nv_bfloat16* __restrict__ dQ, long long total8) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int x = static_cast<int>(e % D);
+    const long long row = e / D;
+    const int n = static_cast<int>(row % N);
+    const long long bh = row / N;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(acc + e));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(acc + e + 4));
+    uint4 o;
+    o.x = pack_bf16x2(a.x * scale, a.y * scale);
+    o.y = pack_bf16x2(a.z * scale, a.w * scale);
+    o.z = pack_bf16x2(b.x * scale, b.y * scale);
+    o.w = pack_bf16x2(b.z * scale, b.w * scale);
+    *reinterpret_cast<uint4*>(dQ + (bh / H) * sb + (bh % H) * sh + static_cast<long long>(n) * sn + x) = o;
+  }
+}
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(384, 1)
+    bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+               const BwdParams p) {
+  using Cfg = BwdCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0 && (smem - smem_raw) + Cfg::SMEM_USED > Cfg::SMEM_BYTES) {
+    printf("fa bwd: dynamic shared memory base misaligned by %d bytes\n", (int)(smem - smem_raw));
+    __trap();
+  }
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sdO = smem + Cfg::OFF_DO;
+  uint8_t* sdS = smem + Cfg::OFF_DS;
+  float* sVec = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);  // [stage][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* kv_full = bars;          // [1]
+  uint64_t* qdo_full = bars + 1;     // [2]
+  uint64_t* qdo_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;       // [2]  (index = iteration parity)
+  uint64_t* p_full = bars + 7;       // [2]
+  uint64_t* dp_full = bars + 9;      // [2]
+  uint64_t* ds_full = bars + 11;     // [2]
+  uint64_t* ds_empty = bars + 13;    // [2]
+  uint64_t* dq_full = bars + 15;     // [2]
+  uint64_t* dq_free = bars + 17;     // [2]
+  uint64_t* dkv_done = bars + 19;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kt * 128;
+  int kv_end = p.N;
+  if (p.kv_len) kv_end = min(kv_end, max(__ldg(p.kv_len + b), 0));
+  const int nq = (p.N + 127) >> 7;
+  const int q_first = CAUSAL ? kt : 0;
+  const int n_iter = nq - q_first;
+  __nv_bfloat16* dKb = reinterpret_cast<__nv_bfloat16*>(p.dK) + b * p.sb + h * p.sh;
+  __nv_bfloat16* dVb = reinterpret_cast<__nv_bfloat16*>(p.dV) + b * p.sb + h * p.sh;
+
+  if (k0 >= kv_end) {
+    // every key of this tile is padding: its gradients are exactly zero
+    for (int idx = threadIdx.x; idx < 128 * (D / 8); idx += blockDim.x) {
+      const int r = idx / (D / 8), c = (idx % (D / 8)) * 8;
+      if (k0 + r < p.N) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dKb + static_cast<long long>(k0 + r) * p.sn + c) = z;
+        *reinterpret_cast<uint4*>(dVb + static_cast<long long>(k0 + r) * p.sn + c) = z;
+      }
+    }
+    return;
+  }
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    mbar_init(dkv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&dp_full[i], 1);
+      mbar_init(&ds_full[i], 128);
+      mbar_init(&ds_empty[i], 1);
+      mbar_init(&dq_full[i], 1);
+      mbar_init(&dq_free[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    reg_dealloc<88>();
+    if (warp == 8) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::NCHUNK; ++c) {
+          tma_load_4d(sK + c * Cfg::CHUNK_BYTES, &tmK, kv_full, c * 64, k0, h, b);
+          tma_load_4d(sV + c * Cfg::CHUNK_BYTES, &tmV, kv_full, c * 64, k0, h, b);
+        }
+        const long long vec_base = (static_cast<long long>(b) * p.H + h) * p.Npad;
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it & 1;
+          const int q0 = (q_first + it) * 128;
+          mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&qdo_full[s], 2 * Cfg::TILE_BYTES + 1024);
+#pragma unroll
+          for (int c = 0; c < Cfg::NCHUNK; ++c) {
+            tma_load_4d(sQ + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQ, &qdo_full[s], c * 64, q0, h, b);
+            tma_load_4d(sdO + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmdO, &qdo_full[s], c * 64, q0, h, b);
+          }
+          bulk_load_1d(sVec + s * 256, p.lse2 + vec_base + q0, 512, &qdo_full[s]);
+          bulk_load_1d(sVec + s * 256 + 128, p.dvec + vec_base + q0, 512, &qdo_full[s]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 9) {
+      // ---------------------------------------------------------------- MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_kn = make_idesc_bf16(128, D, 0, 1);   // A K-major / TMEM, B MN-major
+        constexpr uint32_t idesc_mn = make_idesc_bf16(128, D, 1, 1);   // A MN-major, B MN-major
+        const uint32_t tS = tmem_base + Cfg::T_S, tdP = tmem_base + Cfg::T_DP;
+        const uint32_t tdV = tmem_base + Cfg::T_DV, tdK = tmem_base + Cfg::T_DK;
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sdS);
+        // [128 x 128] = X[128 x D] * Y[128 x D]^T : both operands K-major over the head dim
+        auto issue_nt = [&](uint32_t dst, uint32_t xa, uint32_t ya) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32;
+            mma_ss(dst, make_smem_desc(xa + off, 16, 1024), make_smem_desc(ya + off, 16, 1024), idesc_s, k > 0);
+          }
+        };
+        mbar_wait(kv_full, 0);
+        mbar_wait(&qdo_full[0], 0);
+        tc_fence_after();
+        issue_nt(tS, aK, smem_u32(sQ));
+        mma_commit(&s_full[0]);
+        issue_nt(tdP, aV, smem_u32(sdO));
+        mma_commit(&dp_full[0]);
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it & 1, ph = (it >> 1) & 1;
+          const uint32_t aQ = smem_u32(sQ + s * Cfg::TILE_BYTES), adO = smem_u32(sdO + s * Cfg::TILE_BYTES);
+          // dV += P^T dO_i : A = P^T in TMEM (bf16, 8 columns per 16 queries), B = dO_i as [K=q][N=d]
+          mbar_wait(&p_full[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_ts(tdV, tS + k * 8, make_smem_desc(adO + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn,
+                   (it > 0 || k > 0) ? 1u : 0u);
+          if (it + 1 < n_iter) {
+            const int s1 = (it + 1) & 1;
+            mbar_wait(&qdo_full[s1], ((it + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_nt(tS, aK, smem_u32(sQ + s1 * Cfg::TILE_BYTES));
+            mma_commit(&s_full[s1]);
+          }
+          mbar_wait(&ds_full[s], ph);
+          tc_fence_after();
+          // dQ_i = dS K : A = dS^T tile read MN-major ([K=key][M=q]), B = K tile as [K=key][N=d]
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_ss(tdP, make_smem_desc(aDS + k * 2048, Cfg::CHUNK_BYTES, 1024),
+                   make_smem_desc(aK + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_mn, k > 0);
+          mma_commit(&dq_full[s]);
+          // dK += dS^T Q_i : A = dS^T tile K-major ([M=key][K=q]), B = Q_i as [K=q][N=d]
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_ss(tdK, make_smem_desc(aDS + (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32, 16, 1024),
+                   make_smem_desc(aQ + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+          mma_commit(&ds_empty[s]);
+          mma_commit(&qdo_empty[s]);
+          if (it + 1 < n_iter) {
+            const int s1 = (it + 1) & 1;
+            mbar_wait(&dq_free[s], ph);
+            tc_fence_after();
+            issue_nt(tdP, aV, smem_u32(sdO + s1 * Cfg::TILE_BYTES));
+            mma_commit(&dp_full[s1]);
+          }
+        }
+        mma_commit(dkv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ compute groups
+    reg_alloc<208>();
+    const int g = warp >> 2, w = warp & 3;
+    const int j = w * 32 + lane;                 // key row of this thread == its TMEM lane
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
+    const uint32_t tS = lane_base + Cfg::T_S, tdP = lane_base + Cfg::T_DP;
+    const bool key_ok = (k0 + j) < kv_end;
+    uint8_t* ds_row = sdS + j * 128;
+    const int jx = j & 7;
+    float* dq_bh = p.dq_acc + (static_cast<long long>(b) * p.H + h) * p.N * D;
+
+    for (int it = g; it < n_iter; it += 2) {
+      const int ph = (it >> 1) & 1;
+      const int q0 = (q_first + it) * 128;
+      const float* lse = sVec + g * 256;
+      const float* dv = lse + 128;
+      // ---- P^T = exp2(S^T * scale*log2e - LSE2[q])
+      mbar_wait(&s_full[g], ph);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tS + 32 * c, u);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[32 * c + i] = __uint_as_float(u[i]);
+      }
+      tmem_wait_ld();
+      mbar_wait(&qdo_full[g], ph);  // LSE / D vectors of this Q tile are in shared memory
+      int cmin = 0;                 // causal: queries q0+c < key are masked
+      if (CAUSAL) cmin = k0 + j - q0;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c4 = 0; c4 < 32; ++c4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lse + 4 * c4);
+        float e0 = ex2_approx(fmaf(s[4 * c4 + 0], p.scale_log2, -l4.x));
+        float e1 = ex2_approx(fmaf(s[4 * c4 + 1], p.scale_log2, -l4.y));
+        float e2 = ex2_approx(fmaf(s[4 * c4 + 2], p.scale_log2, -l4.z));
+        float e3 = ex2_approx(fmaf(s[4 * c4 + 3], p.scale_log2, -l4.w));
+        if (!key_ok || (CAUSAL && 4 * c4 + 0 < cmin)) e0 = 0.f;
+        if (!key_ok || (CAUSAL && 4 * c4 + 1 < cmin)) e1 = 0.f;
+        if (!key_ok || (CAUSAL && 4 * c4 + 2 < cmin)) e2 = 0.f;
+        if (!key_ok || (CAUSAL && 4 * c4 + 3 < cmin)) e3 = 0.f;
+        pk[2 * c4] = pack_bf16x2(e0, e1);
+        pk[2 * c4 + 1] = pack_bf16x2(e2, e3);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tmem_st32(tS + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&pk[32 * c]));
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+
+      // ---- dS^T = P^T * (dP^T - D[q])  -> shared memory (bf16, 128B-swizzled rows)
+      mbar_wait(&dp_full[g], ph);
+      tc_fence_after();
+      if (it >= 1) mbar_wait(&ds_empty[g ^ 1], ((it - 1) >> 1) & 1);  // dK(it-1) done with the buffer
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tdP + 32 * c, u);
+        tmem_wait_ld();
+        if (c == 3) tc_fence_before();
+#pragma unroll
+        for (int v8 = 0; v8 < 4; ++v8) {   // 8 queries -> one 16-byte piece
+          uint32_t o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = 32 * c + 8 * v8 + 2 * t;
+            const uint32_t pp = pk[col >> 1];
+            const float p0 = __uint_as_float(pp << 16), p1 = __uint_as_float(pp & 0xffff0000u);
+            const float2 d2 = *reinterpret_cast<const float2*>(dv + col);
+            const float ds0 = p0 * (__uint_as_float(u[8 * v8 + 2 * t]) - d2.x);
+            const float ds1 = p1 * (__uint_as_float(u[8 * v8 + 2 * t + 1]) - d2.y);
+            o[t] = pack_bf16x2(ds0, ds1);
+          }
+          const int unit = 4 * (c & 1) + v8;  // 16-byte unit inside the 128-byte row of this chunk
+          *reinterpret_cast<uint4*>(ds_row + (c >> 1) * Cfg::CHUNK_BYTES + ((unit ^ jx) << 4)) =
+              make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&ds_full[g]);
+
+      // ---- drain dQ_i (lane = query row) into the fp32 accumulator
+      mbar_wait(&dq_full[g], ph);
+      tc_fence_after();
+      const int q = q0 + j;
+      float* dq_row = dq_bh + static_cast<long long>(q) * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tdP + 32 * c, u);
+        tmem_wait_ld();
+        if (c == D / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(&dq_free[g]);
+        }
+        if (q < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            red_add_v4(dq_row + 32 * c + 4 * i, __uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
+                       __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3]));
+        }
+      }
+    }
+
+    // ---- epilogue: group 0 stores dK (scaled), group 1 stores dV
+    mbar_wait(dkv_done, 0);
+    tc_fence_after();
+    const uint32_t tacc = lane_base + (g == 0 ? Cfg::T_DK : Cfg::T_DV);
+    const float mul = (g == 0) ? p.scale : 1.0f;
+    __nv_bfloat16* orow = (g == 0 ? dKb : dVb) + static_cast<long long>(k0 + j) * p.sn;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t u[32];
+      tmem_ld32(tacc + 32 * c, u);
+      tmem_wait_ld();
+      if (k0 + j < p.N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(u[8 * i]) * mul, __uint_as_float(u[8 * i + 1]) * mul);
+          o.y = pack_bf16x2(__uint_as_float(u[8 * i + 2]) * mul, __uint_as_float(u[8 * i + 3]) * mul);
+          o.z = pack_bf16x2(__uint_as_float(u[8 * i + 4]) * mul, __uint_as_float(u[8 * i + 5]) * mul);
+          o.w = pack_bf16x2(__uint_as_float(u[8 * i + 6]) * mul, __uint_as_float(u[8 * i + 7]) * mul);
+          *reinterpret_cast<uint4*>(orow + 32 * c + 8 * i) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace sm100

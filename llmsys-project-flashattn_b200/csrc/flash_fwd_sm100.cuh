@@ -36,14 +36,13 @@ struct FwdParams {
   float scale_log2;       // scale * log2(e)
 };
 
-template <int D, int PMODE>
+template <int D>
 struct FwdCfg {
   static constexpr int NCHUNK = D / 64;            // 128-byte swizzle chunks per row
   static constexpr int CHUNK_BYTES = 128 * 128;    // [128 rows][64 bf16]
   static constexpr int TILE_BYTES = NCHUNK * CHUNK_BYTES;
-  static constexpr int P_BYTES = (PMODE == 1) ? 2 * CHUNK_BYTES : 0;  // debug: P through smem
-  static constexpr int NSTAGE = (PMODE == 1) ? 2 : ((D == 128) ? 5 : 8);
-  static constexpr int SMEM_TILES = 2 * TILE_BYTES + NSTAGE * TILE_BYTES + 2 * P_BYTES;
+  static constexpr int NSTAGE = (D == 128) ? 5 : 8;
+  static constexpr int SMEM_TILES = 2 * TILE_BYTES + NSTAGE * TILE_BYTES;
   static constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
   static constexpr int NTHREADS = 384;
@@ -78,17 +77,16 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
 }
 
 // MASKMODE: 0 none (N-ragged only), 1 kv_len[b], 2 additive key mask (B,N)
-template <int D, bool CAUSAL, int MASKMODE, typename OutT, int PMODE>
+template <int D, bool CAUSAL, int MASKMODE, typename OutT>
 __global__ void __launch_bounds__(384, 1)
     fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
-  using Cfg = FwdCfg<D, PMODE>;
+  using Cfg = FwdCfg<D>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2][TILE_BYTES]
   uint8_t* sKV = smem + 2 * Cfg::TILE_BYTES;            // [NSTAGE][TILE_BYTES]
-  uint8_t* sP = sKV + NSTAGE * Cfg::TILE_BYTES;         // [2][P_BYTES] (PMODE 1 only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);
   uint64_t* q_full = bars;                 // [2]
   uint64_t* kv_full = bars + 2;            // [NSTAGE]
@@ -181,18 +179,13 @@ __global__ void __launch_bounds__(384, 1)
           mma_ss(tS[g], make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk, k > 0);
         }
       };
-      // O_g += P_g V : A = P (TMEM, or smem K-major in PMODE 1), B = V tile (MN-major), 16 keys per MMA
+      // O_g += P_g V : A = P (bf16 in TMEM, 8 columns per 16 keys), B = V tile (MN-major), 16 keys per MMA
       auto issue_pv = [&](int g, int t, bool acc) {
         const uint32_t va = stage_addr(t);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t bdesc = make_smem_desc(va + k * 2048, Cfg::CHUNK_BYTES, 1024);
-          if (PMODE == 0) {
-            mma_ts(tO[g], tS[g] + k * 8, bdesc, idesc_pv, (acc || k > 0) ? 1u : 0u);
-          } else {
-            const uint32_t pa = smem_u32(sP + g * Cfg::P_BYTES) + (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32;
-            mma_ss(tO[g], make_smem_desc(pa, 16, 1024), bdesc, idesc_pv, (acc || k > 0) ? 1u : 0u);
-          }
+          mma_ts(tO[g], tS[g] + k * 8, bdesc, idesc_pv, (acc || k > 0) ? 1u : 0u);
         }
       };
       wait_full(0);
@@ -317,33 +310,15 @@ __global__ void __launch_bounds__(384, 1)
           rs += s[i];
         }
         l_run += rs;
-        if (PMODE == 0) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t pk[32];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[64 * c + 2 * i], s[64 * c + 2 * i + 1]);
-            tmem_st32(tS + 32 * c, pk);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-        } else {
-          // debug path: P -> shared memory in the K-major 128B-swizzled layout of an A operand
-          uint8_t* prow = sP + g * Cfg::P_BYTES + (w * 32 + lane) * 128;
-          const int rx = (w * 32 + lane) & 7;
-#pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            uint4 v;
-            v.x = pack_bf16x2(s[8 * u], s[8 * u + 1]);
-            v.y = pack_bf16x2(s[8 * u + 2], s[8 * u + 3]);
-            v.z = pack_bf16x2(s[8 * u + 4], s[8 * u + 5]);
-            v.w = pack_bf16x2(s[8 * u + 6], s[8 * u + 7]);
-            *reinterpret_cast<uint4*>(prow + (u >> 3) * Cfg::CHUNK_BYTES + (((u & 7) ^ rx) << 4)) = v;
-          }
-          tmem_wait_st();
-          fence_proxy_async_smem();
-          tc_fence_before();
+          for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[64 * c + 2 * i], s[64 * c + 2 * i + 1]);
+          tmem_st32(tS + 32 * c, pk);
         }
+        tmem_wait_st();
+        tc_fence_before();
         mbar_arrive(&p_full[g]);
       }
       // epilogue: O / l -> global, statistics
@@ -362,7 +337,7 @@ __global__ void __launch_bounds__(384, 1)
       if (row < p.N) {
         const float m_out = (MASKMODE == 2) ? m_true * (1.0f / LOG2E) : m_true * p.scale;
         p.M[stat_idx] = m_out;
-        p.L[stat_idx] = l_run * ex2_approx((m_used - m_true) * sc);
+        p.L[stat_idx] = (m_true == -INFINITY) ? 0.f : l_run * ex2_approx((m_used - m_true) * sc);
       }
     }
   }

@@ -19,14 +19,11 @@
 namespace fa {
 
 static int g_mode = -1;  // resolved lazily from MINITORCH_FA_MODE
-static int g_pmode = 0;  // debug: FA_PMODE=1 routes P through shared memory instead of TMEM
 
 static int current_mode() {
   if (g_mode < 0) {
     const char* e = getenv("MINITORCH_FA_MODE");
     g_mode = (e && (!strcmp(e, "bf16") || !strcmp(e, "BF16"))) ? FA_MODE_BF16 : FA_MODE_FP32;
-    const char* pm = getenv("FA_PMODE");
-    g_pmode = (pm && pm[0] == '1') ? 1 : 0;
   }
   return g_mode;
 }
@@ -120,6 +117,7 @@ static int fwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const v
   auto launch = [&](auto kern) -> int {
     FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32k::kSmemFwd));
     kern<<<grid, f32k::NT, f32k::kSmemFwd, st>>>(p, (const T*)Q, (const T*)K, (const T*)V, (T*)O, m, l);
+    fa::count_launch();
     FA_CUDA_CHECK(cudaGetLastError());
     return FA_OK;
   };
@@ -135,6 +133,7 @@ static int bwd_prep(const AttnParams& p, const void* O, const void* dO, const fl
   long long blocks = (rows + 7) / 8;
   if (blocks > 148 * 32) blocks = 148 * 32;
   f32k::bwd_prep_kernel<T><<<(int)blocks, 256, 0, st>>>(p, (const T*)O, (const T*)dO, m, l, Dv, LSE);
+    fa::count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;
 }
@@ -159,6 +158,7 @@ static int bwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const v
       FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32k::kSmemBwd));
       kern<<<grid, f32k::NT, f32k::kSmemBwd, st>>>(p, (const T*)Q, (const T*)K, (const T*)V, (const T*)dO, Dv, LSE,
                                                    (T*)dK, (T*)dV);
+    fa::count_launch();
       FA_CUDA_CHECK(cudaGetLastError());
       return FA_OK;
     };
@@ -174,6 +174,7 @@ static int bwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const v
       FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32k::kSmemBwd));
       kern<<<grid, f32k::NT, f32k::kSmemBwd, st>>>(p, (const T*)Q, (const T*)K, (const T*)V, (const T*)dO, Dv, LSE,
                                                    (T*)dQ);
+    fa::count_launch();
       FA_CUDA_CHECK(cudaGetLastError());
       return FA_OK;
     };
@@ -184,14 +185,15 @@ static int bwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const v
 }
 
 // ------------------------------------------------------------------------------ tensor-core path
-template <int D, bool CAUSAL, int MASKMODE, typename OutT, int PMODE>
+template <int D, bool CAUSAL, int MASKMODE, typename OutT>
 static int launch_fwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const sm100::FwdParams& fp, cudaStream_t st) {
-  using Cfg = sm100::FwdCfg<D, PMODE>;
-  auto kern = sm100::fwd_kernel<D, CAUSAL, MASKMODE, OutT, PMODE>;
+  using Cfg = sm100::FwdCfg<D>;
+  auto kern = sm100::fwd_kernel<D, CAUSAL, MASKMODE, OutT>;
   FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((a->N + 255) / 256, a->H, a->B);
   kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, fp);
+    fa::count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;
 }
@@ -219,18 +221,82 @@ static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   fp.scale = 1.0f / sqrtf((float)a->d);
   fp.scale_log2 = fp.scale * 1.4426950408889634f;
   const int maskmode = a->key_mask ? 2 : (a->kv_len ? 1 : 0);
-  current_mode();
-  const int pmode = g_pmode;
-#define FA_FWD_CASE(DD, CC, MM)                                                                   \
-  if (a->d == DD && (a->causal != 0) == CC && maskmode == MM) {                                   \
-    return pmode ? launch_fwd_tc<DD, CC, MM, OutT, 1>(a, tq, tk, tv, fp, st)                      \
-                 : launch_fwd_tc<DD, CC, MM, OutT, 0>(a, tq, tk, tv, fp, st);                     \
-  }
+#define FA_FWD_CASE(DD, CC, MM) \
+  if (a->d == DD && (a->causal != 0) == CC && maskmode == MM) return launch_fwd_tc<DD, CC, MM, OutT>(a, tq, tk, tv, fp, st);
   FA_FWD_CASE(128, false, 0) FA_FWD_CASE(128, true, 0) FA_FWD_CASE(128, false, 1) FA_FWD_CASE(128, true, 1)
   FA_FWD_CASE(128, false, 2) FA_FWD_CASE(128, true, 2) FA_FWD_CASE(64, false, 0) FA_FWD_CASE(64, true, 0)
   FA_FWD_CASE(64, false, 1) FA_FWD_CASE(64, true, 1) FA_FWD_CASE(64, false, 2) FA_FWD_CASE(64, true, 2)
 #undef FA_FWD_CASE
   return set_error(FA_ERR_UNSUPPORTED, "flash fwd (tensor core): head_dim %d not supported", a->d);
+}
+
+template <int D, bool CAUSAL>
+static int launch_bwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const CUtensorMap& tdo, const sm100::BwdParams& bp, cudaStream_t st) {
+  using Cfg = sm100::BwdCfg<D>;
+  auto kern = sm100::bwd_kernel<D, CAUSAL>;
+  FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  dim3 grid((a->N + 127) / 128, a->H, a->B);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, bp);
+  fa::count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+// Tensor-core backward (bf16, head_dim 64/128, kv_len or no mask).  Returns FA_ERR_UNSUPPORTED for
+// configurations it does not cover (generic additive key mask) so the caller can use the CUDA-core path.
+static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                  const float* m, const float* l, void* dQ, void* dK, void* dV, cudaStream_t st) {
+  if (a->key_mask) return FA_ERR_UNSUPPORTED;
+  Strides s = resolve_strides(a);
+  const int Npad = ((a->N + 127) / 128) * 128;
+  const size_t rows_pad = (size_t)a->B * a->H * Npad;
+  const size_t nacc = (size_t)a->B * a->H * a->N * a->d;
+  float* ws = static_cast<float*>(g_pool.get(13, sizeof(float) * 2 * rows_pad));
+  float* acc = static_cast<float*>(g_pool.get(14, sizeof(float) * nacc));
+  if (!ws || !acc) return set_error(FA_ERR_CUDA, "flash bwd: workspace allocation failed");
+  float *lse2 = ws, *dvec = ws + rows_pad;
+  FA_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(float) * nacc, st));
+  {
+    long long blocks = ((long long)rows_pad + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    sm100::bwd_prep_tc_kernel<<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, a->d, s.sb, s.sh, s.sn,
+                                                           (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, m, l,
+                                                           lse2, dvec);
+    fa::count_launch();
+    FA_CUDA_CHECK(cudaGetLastError());
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  const void* src[4] = {Q, K, V, dO};
+  CUtensorMap* tm[4] = {&tq, &tk, &tv, &tdo};
+  for (int i = 0; i < 4; ++i)
+    if ((rc = make_tmap(tm[i], src[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, a->H, a->N, a->d, s.sb, s.sh, s.sn, 64,
+                        128)))
+      return rc;
+  sm100::BwdParams bp;
+  bp.B = a->B, bp.H = a->H, bp.N = a->N, bp.Npad = Npad;
+  bp.kv_len = a->kv_len;
+  bp.lse2 = lse2, bp.dvec = dvec, bp.dq_acc = acc;
+  bp.dK = dK, bp.dV = dV;
+  bp.sb = s.sb, bp.sh = s.sh, bp.sn = s.sn;
+  bp.scale = 1.0f / sqrtf((float)a->d);
+  bp.scale_log2 = bp.scale * 1.4426950408889634f;
+  if (a->d == 128) rc = a->causal ? launch_bwd_tc<128, true>(a, tq, tk, tv, tdo, bp, st)
+                                  : launch_bwd_tc<128, false>(a, tq, tk, tv, tdo, bp, st);
+  else rc = a->causal ? launch_bwd_tc<64, true>(a, tq, tk, tv, tdo, bp, st)
+                      : launch_bwd_tc<64, false>(a, tq, tk, tv, tdo, bp, st);
+  if (rc) return rc;
+  {
+    const long long total8 = (long long)nacc / 8;
+    long long blocks = (total8 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sm100::bwd_convert_dq_kernel<<<(int)blocks, 256, 0, st>>>(a->H, a->N, a->d, s.sb, s.sh, s.sn, bp.scale, acc,
+                                                              (__nv_bfloat16*)dQ, total8);
+    fa::count_launch();
+    FA_CUDA_CHECK(cudaGetLastError());
+  }
+  return FA_OK;
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
@@ -282,17 +348,13 @@ void fa_set_mode(int mode) {
   g_mode = (mode == FA_MODE_BF16) ? FA_MODE_BF16 : FA_MODE_FP32;
 }
 int fa_get_mode(void) { return current_mode(); }
-// debug only (not part of the public header): 1 routes P through shared memory instead of TMEM
-void fa_debug_set_pmode(int pmode) {
-  current_mode();
-  g_pmode = pmode ? 1 : 0;
-}
 
 int fa_cast_f32_to_bf16_dev(const float* src, void* dst, size_t n, fa_stream_t stream) {
   clear_error();
   if (n == 0) return FA_OK;
   cast_f32_bf16_kernel<<<cast_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), n);
+    fa::count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;
 }
@@ -301,6 +363,7 @@ int fa_cast_bf16_to_f32_dev(const void* src, float* dst, size_t n, fa_stream_t s
   if (n == 0) return FA_OK;
   cast_bf16_f32_kernel<<<cast_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), dst, n);
+    fa::count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;
 }
@@ -342,7 +405,7 @@ int fa_flash_bwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->dtype == FA_DTYPE_F32) return bwd_simt<float>(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
   if (tc_supported(a)) {
-    int r2 = sm100::bwd_tc(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
+    int r2 = bwd_tc(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
     if (r2 != FA_ERR_UNSUPPORTED) return r2;
     clear_error();
   }
@@ -352,6 +415,47 @@ int fa_flash_bwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const 
 // ---------------------------------------------------------------------------------------------
 // Legacy host-pointer ABI.  fp32 host buffers in, fp32 host buffers out.
 // ---------------------------------------------------------------------------------------------
+// A LightSeq-style padding mask is "0 on the first kv_len[b] keys, a huge negative number after"
+// (kernel_tests/test_softmax_fw.py:44-45 uses -1e8).  When every row of the host mask has that
+// shape (tail <= -1e6, at least one valid key) the kernels can skip whole KV tiles through
+// kv_len[] instead of adding the mask element by element; otherwise the generic path is used.
+static bool mask_to_kv_len(const float* key_mask, int B, int N, int* kv_len_out) {
+  for (int b = 0; b < B; ++b) {
+    const float* r = key_mask + (size_t)b * N;
+    int n = 0;
+    while (n < N && r[n] == 0.0f) ++n;
+    if (n == 0) return false;
+    for (int j = n; j < N; ++j)
+      if (!(r[j] <= -1e6f)) return false;
+    kv_len_out[b] = n;
+  }
+  return true;
+}
+// Upload either kv_len[] (fast path) or the additive mask into the descriptor.
+static int stage_mask(fa_attn_desc* a, const float* key_mask, int slot) {
+  if (!key_mask) return FA_OK;
+  const size_t bytes = (size_t)a->B * a->N * 4 + (size_t)a->B * 4 + 16;
+  char* d = static_cast<char*>(g_pool.get(slot, bytes));
+  if (!d) return set_error(FA_ERR_CUDA, "mask staging allocation failed");
+  static int* h_kv = nullptr;
+  static int h_cap = 0;
+  if (h_cap < a->B) {
+    free(h_kv);
+    h_kv = static_cast<int*>(malloc(sizeof(int) * a->B));
+    h_cap = a->B;
+  }
+  if (mask_to_kv_len(key_mask, a->B, a->N, h_kv)) {
+    FA_CUDA_CHECK(cudaMemcpyAsync(d, h_kv, (size_t)a->B * 4, cudaMemcpyHostToDevice, 0));
+    FA_CUDA_CHECK(cudaStreamSynchronize(0));  // h_kv is reused by the next call
+    a->kv_len = reinterpret_cast<const int*>(d);
+  } else {
+    char* dm = d + (((size_t)a->B * 4 + 15) & ~size_t(15));
+    FA_CUDA_CHECK(cudaMemcpyAsync(dm, key_mask, (size_t)a->B * a->N * 4, cudaMemcpyHostToDevice, 0));
+    a->key_mask = reinterpret_cast<const float*>(dm);
+  }
+  return FA_OK;
+}
+
 static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, float* m, const float* key_mask,
                            int causal, int B, int nh, int N, int d) {
   clear_error();
@@ -364,12 +468,12 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
   float* dK_ = static_cast<float*>(g_pool.get(1, n * 4));
   float* dV_ = static_cast<float*>(g_pool.get(2, n * 4));
   float* dO_ = static_cast<float*>(g_pool.get(3, n * 4));
-  float* dml = static_cast<float*>(g_pool.get(4, 2 * r * 4 + (size_t)B * N * 4));
+  float* dml = static_cast<float*>(g_pool.get(4, 2 * r * 4));
   if (!dQ_ || !dK_ || !dV_ || !dO_ || !dml) {
     set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed (%zu bytes per tensor)", n * 4);
     return;
   }
-  float *dm = dml, *dl = dml + r, *dmask = dml + 2 * r;
+  float *dm = dml, *dl = dml + r;
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) {
     if (e == cudaSuccess) e = x;
@@ -377,10 +481,7 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
   step(cudaMemcpyAsync(dQ_, Q, n * 4, cudaMemcpyHostToDevice, 0));
   step(cudaMemcpyAsync(dK_, K, n * 4, cudaMemcpyHostToDevice, 0));
   step(cudaMemcpyAsync(dV_, V, n * 4, cudaMemcpyHostToDevice, 0));
-  if (key_mask) {
-    step(cudaMemcpyAsync(dmask, key_mask, (size_t)B * N * 4, cudaMemcpyHostToDevice, 0));
-    a.key_mask = dmask;
-  }
+  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
   if (e != cudaSuccess) {
     set_error(FA_ERR_CUDA, "launch_flashattention_forward: H2D: %s", cudaGetErrorString(e));
     return;
@@ -448,12 +549,12 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
       return;
     }
   }
-  float* dml = static_cast<float*>(g_pool.get(9, 2 * r * 4 + (size_t)B * N * 4));
+  float* dml = static_cast<float*>(g_pool.get(9, 2 * r * 4));
   if (!dml) {
     set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed");
     return;
   }
-  float *dm = dml, *dl = dml + r, *dmask = dml + 2 * r;
+  float *dm = dml, *dl = dml + r;
   float *gQ = buf[0], *gK = buf[1], *gV = buf[2], *gO = buf[3], *gdO = buf[4], *gdQ = buf[5], *gdK = buf[6],
         *gdV = buf[7];
   cudaError_t e = cudaSuccess;
@@ -467,10 +568,7 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
   step(cudaMemcpyAsync(gdO, dO, n * 4, cudaMemcpyHostToDevice, 0));
   step(cudaMemcpyAsync(dm, m, r * 4, cudaMemcpyHostToDevice, 0));
   step(cudaMemcpyAsync(dl, l, r * 4, cudaMemcpyHostToDevice, 0));
-  if (key_mask) {
-    step(cudaMemcpyAsync(dmask, key_mask, (size_t)B * N * 4, cudaMemcpyHostToDevice, 0));
-    a.key_mask = dmask;
-  }
+  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
   if (e != cudaSuccess) {
     set_error(FA_ERR_CUDA, "launch_flashattention_backward: H2D: %s", cudaGetErrorString(e));
     return;

@@ -64,10 +64,15 @@ struct ScratchPool {
 };
 static ScratchPool g_pool;
 
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+static unsigned long long g_launches = 0;
+inline void count_launch(int n = 1) { g_launches += static_cast<unsigned long long>(n); }
+
 }  // namespace fa
 
 extern "C" {
 int fa_last_status(void) { return fa::g_status; }
+unsigned long long fa_launch_count(void) { return fa::g_launches; }
 const char* fa_last_error(void) { return fa::g_errmsg; }
 int fa_device_count(void) {
   int n = 0;

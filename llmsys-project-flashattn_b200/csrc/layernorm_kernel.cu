@@ -284,6 +284,7 @@ int fa_layernorm_dev(float* ln_res, float* vars, float* means, const float* inp,
     int grid = static_cast<int>(need < cap ? need : cap);
     fa::layernorm_fw_kernel<BLOCK, TPR, ITERS>
         <<<grid, BLOCK, 0, s>>>(ln_res, vars, means, inp, scale, bias, rows, hidden_dim);
+    fa::count_launch();
   });
   if (!ok) return fa::set_error(FA_ERR_UNSUPPORTED, "layernorm: hidden_dim %d > 16384", hidden_dim);
   FA_CUDA_CHECK(cudaGetLastError());
@@ -324,8 +325,10 @@ int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, c
     size_t smem = (RPC > 1) ? sizeof(float) * 2 * RPC * hidden_dim : 0;
     fa::layernorm_bw_kernel<BLOCK, TPR, ITERS><<<grid, BLOCK, smem, s>>>(inp_grad, part_g, part_b, out_grad, inp,
                                                                          gamma, vars, means, rows, hidden_dim);
+    fa::count_launch();
     fa::ln_bw_reduce_kernel<<<(hidden_dim + 255) / 256, 256, 0, s>>>(gamma_grad, betta_grad, part_g, part_b, grid,
                                                                      hidden_dim);
+    fa::count_launch();
   });
   if (status != FA_OK) return status;
   if (!ok) return fa::set_error(FA_ERR_UNSUPPORTED, "layernorm_bw: hidden_dim %d > 16384", hidden_dim);

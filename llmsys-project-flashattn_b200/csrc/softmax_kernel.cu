@@ -254,6 +254,7 @@ int fa_attn_softmax_dev(float* inp, const float* attn_mask, int batch_size, int 
   bool ok = fa::dispatch_row(to_len, aligned, [&]<int TPR, int VEC, int ITERS>() {
     fa::attn_softmax_fw_kernel<TPR, VEC, ITERS><<<fa::grid_for(rows, 256 / TPR), 256, 0, s>>>(
         inp, attn_mask, rows, nhead, from_len, to_len, mask_future);
+    fa::count_launch();
   });
   if (!ok) return fa::set_error(FA_ERR_UNSUPPORTED, "attn_softmax: to_len %d > 16384 not supported", to_len);
   FA_CUDA_CHECK(cudaGetLastError());
@@ -272,6 +273,7 @@ int fa_attn_softmax_bw_dev(float* out_grad, const float* soft_inp, long long row
   bool ok = fa::dispatch_row(softmax_len, aligned, [&]<int TPR, int VEC, int ITERS>() {
     fa::attn_softmax_bw_kernel<TPR, VEC, ITERS>
         <<<fa::grid_for(rows, 256 / TPR), 256, 0, s>>>(out_grad, soft_inp, rows, softmax_len);
+    fa::count_launch();
   });
   if (!ok)
     return fa::set_error(FA_ERR_UNSUPPORTED, "attn_softmax_bw: softmax_len %d > 16384 not supported",

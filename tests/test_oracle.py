@@ -84,3 +84,15 @@ def test_bf16_rounding_helpers():
     assert r[0] == 1.0 and r[2] == 1.0078125
     assert r[1] == 1.0  # tie -> even
     np.testing.assert_array_equal(R.from_bf16_bits(R.to_bf16_bits(x)), r)
+
+
+@pytest.mark.parametrize("name", ["attn_cfg1.npz", "attn_cfg1_causal.npz", "attn_n39_causal.npz", "attn_n100.npz"])
+def test_numba_port_matches_reference_composed(name):
+    """oracle/numba_composed.py (the CPU-baseline port) against vectors made by the real reference."""
+    from oracle import numba_composed as NC
+    z = np.load(os.path.join(G, name))
+    O, dQ, dK, dV = NC.attention_fwd_bwd(z["Q"], z["K"], z["V"], z["dO"], causal=bool(z["causal"]))
+    np.testing.assert_allclose(O, z["O"], atol=3e-6, rtol=1e-5)
+    np.testing.assert_allclose(dQ, z["dQ"], atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(dK, z["dK"], atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(dV, z["dV"], atol=3e-5, rtol=1e-4)

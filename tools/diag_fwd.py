@@ -17,8 +17,6 @@ from oracle import attention_ref as R  # noqa: E402
 
 def run(B, H, N, d, causal, pmode, kv=None, mask=False, seed=0):
     lib = fb._lib.load("flashattention_kernel")
-    lib.fa_debug_set_pmode.argtypes = [ctypes.c_int]
-    lib.fa_debug_set_pmode(pmode)
     rng = np.random.default_rng(seed)
     Q, K, V = (R.round_bf16(rng.standard_normal((B, H, N, d)).astype(np.float32)) for _ in range(3))
     kv_len = None
@@ -55,7 +53,7 @@ def run(B, H, N, d, causal, pmode, kv=None, mask=False, seed=0):
 
 
 if __name__ == "__main__":
-    pmodes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "0,1").split(",")]
+    pmodes = [0]
     cases = [
         (1, 1, 128, 128, False, None, False),
         (1, 1, 128, 64, False, None, False),
