@@ -15,14 +15,16 @@
 // Row statistics LSE_i and D_i = rowsum(dO*O) come from a pre-pass (log2 domain, padded so
 // out-of-range queries get P = 0) and arrive per Q tile with the same TMA transaction.
 //   warps 0-3 / 4-7 : two compute groups that alternate Q tiles (ping-pong): exp2 -> P^T,
-//                     dS^T = P^T*(dP^T - D), then drain dQ_i from TMEM into the fp32 dQ
-//                     accumulator in global memory with red.global.add.v4.f32
-//   warp 8          : TMA producer (K,V once; Q_i, dO_i, LSE_i, D_i through a 2-stage ring)
+//                     dS^T = P^T*(dP^T - D), then drain dQ_i: TMEM -> registers -> 128B-swizzled
+//                     staging box in shared memory -> cp.reduce.async.bulk.tensor (fp32 add) into
+//                     the dQ accumulator (LSU red.global tops out near 9 clk per warp instruction
+//                     on B200, far too slow for 64 KB per tile pair)
+//   warp 8          : TMA producer (K,V once; Q_i + LSE_i + D_i 2-stage ring; dO_i single stage)
 //   warp 9          : tcgen05.mma issuer + TMEM allocation
 // The tensor pipe executes in issue order, so single-buffered T_S / T_dP are enough: S^T(i+1)
 // is issued right after dV(i) and overlaps the other group's dS phase.
-// dQ is accumulated across KV-tile CTAs in fp32 (atomic adds; summation order varies between
-// runs) and converted to bf16 * scale by a small kernel afterwards.
+// dQ is accumulated across KV-tile CTAs in fp32 (TMA add-reductions; summation order varies
+// between runs) and converted to bf16 * scale by a small kernel afterwards.
 #pragma once
 #include "ptx.cuh"
 
@@ -47,13 +49,15 @@ struct BwdCfg {
   static constexpr int CHUNK_BYTES = 128 * 128;
   static constexpr int TILE_BYTES = NCHUNK * CHUNK_BYTES;   // K, V, Q_i, dO_i tiles: [128][D] bf16
   static constexpr int DS_BYTES = 2 * CHUNK_BYTES;          // dS^T tile: [128 keys][128 queries] bf16
+  static constexpr int STG_BYTES = 128 * 128;               // dQ staging box per compute group: [128 q][32 fp32]
   static constexpr int VEC_BYTES = 2 * 2 * 512;             // [stage][lse2 | D][128] fp32
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = TILE_BYTES;
   static constexpr int OFF_Q = 2 * TILE_BYTES;              // [2 stages]
-  static constexpr int OFF_DO = 4 * TILE_BYTES;             // [2 stages]
-  static constexpr int OFF_DS = 6 * TILE_BYTES;
-  static constexpr int OFF_VEC = OFF_DS + DS_BYTES;
+  static constexpr int OFF_DO = 4 * TILE_BYTES;             // [1 stage]
+  static constexpr int OFF_DS = 5 * TILE_BYTES;
+  static constexpr int OFF_STG = OFF_DS + DS_BYTES;         // [2 groups]
+  static constexpr int OFF_VEC = OFF_STG + 2 * STG_BYTES;
   static constexpr int OFF_BAR = OFF_VEC + VEC_BYTES;
   static constexpr int SMEM_USED = OFF_BAR + 256;
   static constexpr int SMEM_BYTES = (SMEM_USED + 1024 <= 232448) ? SMEM_USED + 1024 : 232448;
@@ -67,10 +71,6 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
-}
-__device__ __forceinline__ void red_add_v4(float* gptr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
 }
 
 // D_i = sum_x dO*O and LSE_i (log2 domain) for the tensor-core backward; one warp per row,
@@ -131,14 +131,39 @@ __global__ void bwd_convert_dq_kernel(int H, int N, int D, long long sb, long lo
   }
 }
 
+// exp2 of one 4-column group -> two packed bf16x2 registers
+#define FA_BWD_P4(c4, MASKED)                                                              \
+  {                                                                                        \
+    const float4 l4 = *reinterpret_cast<const float4*>(lse + 4 * (c4));                    \
+    float e0 = ex2_approx(fmaf(s[4 * (c4) + 0], p.scale_log2, -l4.x));                     \
+    float e1 = ex2_approx(fmaf(s[4 * (c4) + 1], p.scale_log2, -l4.y));                     \
+    float e2 = ex2_approx(fmaf(s[4 * (c4) + 2], p.scale_log2, -l4.z));                     \
+    float e3 = ex2_approx(fmaf(s[4 * (c4) + 3], p.scale_log2, -l4.w));                     \
+    if (MASKED) {                                                                          \
+      if (!key_ok || 4 * (c4) + 0 < cmin) e0 = 0.f;                                        \
+      if (!key_ok || 4 * (c4) + 1 < cmin) e1 = 0.f;                                        \
+      if (!key_ok || 4 * (c4) + 2 < cmin) e2 = 0.f;                                        \
+      if (!key_ok || 4 * (c4) + 3 < cmin) e3 = 0.f;                                        \
+    }                                                                                      \
+    pk[2 * (c4)] = pack_bf16x2(e0, e1);                                                    \
+    pk[2 * (c4) + 1] = pack_bf16x2(e2, e3);                                                \
+  }
+
+__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(384, 1)
     bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-               const BwdParams p) {
+               const __grid_constant__ CUtensorMap tmdQ, const BwdParams p) {
   using Cfg = BwdCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by offset (not by pointer cast) so the compiler keeps the shared address space: LDS/STS, not LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   if (threadIdx.x == 0 && (smem - smem_raw) + Cfg::SMEM_USED > Cfg::SMEM_BYTES) {
     printf("fa bwd: dynamic shared memory base misaligned by %d bytes\n", (int)(smem - smem_raw));
     __trap();
@@ -148,20 +173,23 @@ __global__ void __launch_bounds__(384, 1)
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sdO = smem + Cfg::OFF_DO;
   uint8_t* sdS = smem + Cfg::OFF_DS;
+  uint8_t* sStg = smem + Cfg::OFF_STG;
   float* sVec = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);  // [stage][2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* kv_full = bars;          // [1]
-  uint64_t* qdo_full = bars + 1;     // [2]
-  uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;       // [2]  (index = iteration parity)
-  uint64_t* p_full = bars + 7;       // [2]
-  uint64_t* dp_full = bars + 9;      // [2]
-  uint64_t* ds_full = bars + 11;     // [2]
-  uint64_t* ds_empty = bars + 13;    // [2]
-  uint64_t* dq_full = bars + 15;     // [2]
-  uint64_t* dq_free = bars + 17;     // [2]
-  uint64_t* dkv_done = bars + 19;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* q_full = bars + 1;       // [2]  Q_i + LSE_i + D_i
+  uint64_t* q_empty = bars + 3;      // [2]
+  uint64_t* do_full = bars + 5;      // [1]  dO_i (single stage)
+  uint64_t* do_empty = bars + 6;     // [1]
+  uint64_t* s_full = bars + 7;       // [2]  (index = iteration parity)
+  uint64_t* p_full = bars + 9;       // [2]
+  uint64_t* dp_full = bars + 11;     // [2]
+  uint64_t* ds_full = bars + 13;     // [2]
+  uint64_t* ds_empty = bars + 15;    // [2]
+  uint64_t* dq_full = bars + 17;     // [2]
+  uint64_t* dq_free = bars + 19;     // [2]
+  uint64_t* dkv_done = bars + 21;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -192,11 +220,14 @@ __global__ void __launch_bounds__(384, 1)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdQ);
     mbar_init(kv_full, 1);
     mbar_init(dkv_done, 1);
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&qdo_full[i], 1);
-      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&dp_full[i], 1);
@@ -228,15 +259,18 @@ __global__ void __launch_bounds__(384, 1)
         for (int it = 0; it < n_iter; ++it) {
           const int s = it & 1;
           const int q0 = (q_first + it) * 128;
-          mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
-          mbar_expect_tx(&qdo_full[s], 2 * Cfg::TILE_BYTES + 1024);
+          mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[s], Cfg::TILE_BYTES + 1024);
 #pragma unroll
-          for (int c = 0; c < Cfg::NCHUNK; ++c) {
-            tma_load_4d(sQ + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQ, &qdo_full[s], c * 64, q0, h, b);
-            tma_load_4d(sdO + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmdO, &qdo_full[s], c * 64, q0, h, b);
-          }
-          bulk_load_1d(sVec + s * 256, p.lse2 + vec_base + q0, 512, &qdo_full[s]);
-          bulk_load_1d(sVec + s * 256 + 128, p.dvec + vec_base + q0, 512, &qdo_full[s]);
+          for (int c = 0; c < Cfg::NCHUNK; ++c)
+            tma_load_4d(sQ + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQ, &q_full[s], c * 64, q0, h, b);
+          bulk_load_1d(sVec + s * 256, p.lse2 + vec_base + q0, 512, &q_full[s]);
+          bulk_load_1d(sVec + s * 256 + 128, p.dvec + vec_base + q0, 512, &q_full[s]);
+          mbar_wait(do_empty, (it & 1) ^ 1);
+          mbar_expect_tx(do_full, Cfg::TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < Cfg::NCHUNK; ++c)
+            tma_load_4d(sdO + c * Cfg::CHUNK_BYTES, &tmdO, do_full, c * 64, q0, h, b);
         }
       }
       __syncwarp();
@@ -248,7 +282,7 @@ __global__ void __launch_bounds__(384, 1)
         constexpr uint32_t idesc_mn = make_idesc_bf16(128, D, 1, 1);   // A MN-major, B MN-major
         const uint32_t tS = tmem_base + Cfg::T_S, tdP = tmem_base + Cfg::T_DP;
         const uint32_t tdV = tmem_base + Cfg::T_DV, tdK = tmem_base + Cfg::T_DK;
-        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sdS);
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sdS), adO = smem_u32(sdO);
         // [128 x 128] = X[128 x D] * Y[128 x D]^T : both operands K-major over the head dim
         auto issue_nt = [&](uint32_t dst, uint32_t xa, uint32_t ya) {
 #pragma unroll
@@ -258,15 +292,17 @@ __global__ void __launch_bounds__(384, 1)
           }
         };
         mbar_wait(kv_full, 0);
-        mbar_wait(&qdo_full[0], 0);
+        mbar_wait(&q_full[0], 0);
         tc_fence_after();
         issue_nt(tS, aK, smem_u32(sQ));
         mma_commit(&s_full[0]);
-        issue_nt(tdP, aV, smem_u32(sdO));
+        mbar_wait(do_full, 0);
+        tc_fence_after();
+        issue_nt(tdP, aV, adO);
         mma_commit(&dp_full[0]);
         for (int it = 0; it < n_iter; ++it) {
           const int s = it & 1, ph = (it >> 1) & 1;
-          const uint32_t aQ = smem_u32(sQ + s * Cfg::TILE_BYTES), adO = smem_u32(sdO + s * Cfg::TILE_BYTES);
+          const uint32_t aQ = smem_u32(sQ + s * Cfg::TILE_BYTES);
           // dV += P^T dO_i : A = P^T in TMEM (bf16, 8 columns per 16 queries), B = dO_i as [K=q][N=d]
           mbar_wait(&p_full[s], ph);
           tc_fence_after();
@@ -274,9 +310,10 @@ __global__ void __launch_bounds__(384, 1)
           for (int k = 0; k < 8; ++k)
             mma_ts(tdV, tS + k * 8, make_smem_desc(adO + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn,
                    (it > 0 || k > 0) ? 1u : 0u);
+          mma_commit(do_empty);   // dO_i is dead once dV(i) has run (dP(i) ran earlier)
           if (it + 1 < n_iter) {
             const int s1 = (it + 1) & 1;
-            mbar_wait(&qdo_full[s1], ((it + 1) >> 1) & 1);
+            mbar_wait(&q_full[s1], ((it + 1) >> 1) & 1);
             tc_fence_after();
             issue_nt(tS, aK, smem_u32(sQ + s1 * Cfg::TILE_BYTES));
             mma_commit(&s_full[s1]);
@@ -295,12 +332,13 @@ __global__ void __launch_bounds__(384, 1)
             mma_ss(tdK, make_smem_desc(aDS + (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32, 16, 1024),
                    make_smem_desc(aQ + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
           mma_commit(&ds_empty[s]);
-          mma_commit(&qdo_empty[s]);
+          mma_commit(&q_empty[s]);
           if (it + 1 < n_iter) {
             const int s1 = (it + 1) & 1;
+            mbar_wait(do_full, (it + 1) & 1);
             mbar_wait(&dq_free[s], ph);
             tc_fence_after();
-            issue_nt(tdP, aV, smem_u32(sdO + s1 * Cfg::TILE_BYTES));
+            issue_nt(tdP, aV, adO);
             mma_commit(&dp_full[s1]);
           }
         }
@@ -312,13 +350,15 @@ __global__ void __launch_bounds__(384, 1)
     // ------------------------------------------------------------------ compute groups
     reg_alloc<208>();
     const int g = warp >> 2, w = warp & 3;
-    const int j = w * 32 + lane;                 // key row of this thread == its TMEM lane
+    const int j = w * 32 + lane;                 // this thread's TMEM lane: key row (S^T, dP^T) / query row (dQ)
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
     const uint32_t tS = lane_base + Cfg::T_S, tdP = lane_base + Cfg::T_DP;
     const bool key_ok = (k0 + j) < kv_end;
+    const bool all_keys_ok = (k0 + 128) <= kv_end;
     uint8_t* ds_row = sdS + j * 128;
+    uint8_t* stg_row = sStg + g * Cfg::STG_BYTES + j * 128;
     const int jx = j & 7;
-    float* dq_bh = p.dq_acc + (static_cast<long long>(b) * p.H + h) * p.N * D;
+    const bool issuer = (w == 0 && lane == 0);   // issues this group's TMA reductions
 
     for (int it = g; it < n_iter; it += 2) {
       const int ph = (it >> 1) & 1;
@@ -337,23 +377,16 @@ __global__ void __launch_bounds__(384, 1)
         for (int i = 0; i < 32; ++i) s[32 * c + i] = __uint_as_float(u[i]);
       }
       tmem_wait_ld();
-      mbar_wait(&qdo_full[g], ph);  // LSE / D vectors of this Q tile are in shared memory
-      int cmin = 0;                 // causal: queries q0+c < key are masked
-      if (CAUSAL) cmin = k0 + j - q0;
+      mbar_wait(&q_full[g], ph);  // LSE / D vectors of this Q tile are in shared memory
       uint32_t pk[64];
+      const bool diag = CAUSAL && (q0 < k0 + 128);
+      const int cmin = CAUSAL ? (k0 + j - q0) : 0;  // causal: queries q0+c < key are masked
+      if (all_keys_ok && !diag) {
 #pragma unroll
-      for (int c4 = 0; c4 < 32; ++c4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(lse + 4 * c4);
-        float e0 = ex2_approx(fmaf(s[4 * c4 + 0], p.scale_log2, -l4.x));
-        float e1 = ex2_approx(fmaf(s[4 * c4 + 1], p.scale_log2, -l4.y));
-        float e2 = ex2_approx(fmaf(s[4 * c4 + 2], p.scale_log2, -l4.z));
-        float e3 = ex2_approx(fmaf(s[4 * c4 + 3], p.scale_log2, -l4.w));
-        if (!key_ok || (CAUSAL && 4 * c4 + 0 < cmin)) e0 = 0.f;
-        if (!key_ok || (CAUSAL && 4 * c4 + 1 < cmin)) e1 = 0.f;
-        if (!key_ok || (CAUSAL && 4 * c4 + 2 < cmin)) e2 = 0.f;
-        if (!key_ok || (CAUSAL && 4 * c4 + 3 < cmin)) e3 = 0.f;
-        pk[2 * c4] = pack_bf16x2(e0, e1);
-        pk[2 * c4 + 1] = pack_bf16x2(e2, e3);
+        for (int c4 = 0; c4 < 32; ++c4) FA_BWD_P4(c4, false)
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 32; ++c4) FA_BWD_P4(c4, true)
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_st32(tS + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&pk[32 * c]));
@@ -373,47 +406,50 @@ __global__ void __launch_bounds__(384, 1)
         if (c == 3) tc_fence_before();
 #pragma unroll
         for (int v8 = 0; v8 < 4; ++v8) {   // 8 queries -> one 16-byte piece
-          uint32_t o[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int col = 32 * c + 8 * v8 + 2 * t;
-            const uint32_t pp = pk[col >> 1];
-            const float p0 = __uint_as_float(pp << 16), p1 = __uint_as_float(pp & 0xffff0000u);
-            const float2 d2 = *reinterpret_cast<const float2*>(dv + col);
-            const float ds0 = p0 * (__uint_as_float(u[8 * v8 + 2 * t]) - d2.x);
-            const float ds1 = p1 * (__uint_as_float(u[8 * v8 + 2 * t + 1]) - d2.y);
-            o[t] = pack_bf16x2(ds0, ds1);
-          }
+          const float4 da = *reinterpret_cast<const float4*>(dv + 32 * c + 8 * v8);
+          const float4 db = *reinterpret_cast<const float4*>(dv + 32 * c + 8 * v8 + 4);
+          uint4 o;
+          o.x = bf16x2_mul(pk[16 * c + 4 * v8 + 0], pack_bf16x2(__uint_as_float(u[8 * v8 + 0]) - da.x,
+                                                                __uint_as_float(u[8 * v8 + 1]) - da.y));
+          o.y = bf16x2_mul(pk[16 * c + 4 * v8 + 1], pack_bf16x2(__uint_as_float(u[8 * v8 + 2]) - da.z,
+                                                                __uint_as_float(u[8 * v8 + 3]) - da.w));
+          o.z = bf16x2_mul(pk[16 * c + 4 * v8 + 2], pack_bf16x2(__uint_as_float(u[8 * v8 + 4]) - db.x,
+                                                                __uint_as_float(u[8 * v8 + 5]) - db.y));
+          o.w = bf16x2_mul(pk[16 * c + 4 * v8 + 3], pack_bf16x2(__uint_as_float(u[8 * v8 + 6]) - db.z,
+                                                                __uint_as_float(u[8 * v8 + 7]) - db.w));
           const int unit = 4 * (c & 1) + v8;  // 16-byte unit inside the 128-byte row of this chunk
-          *reinterpret_cast<uint4*>(ds_row + (c >> 1) * Cfg::CHUNK_BYTES + ((unit ^ jx) << 4)) =
-              make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(ds_row + (c >> 1) * Cfg::CHUNK_BYTES + ((unit ^ jx) << 4)) = o;
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[g]);
 
-      // ---- drain dQ_i (lane = query row) into the fp32 accumulator
+      // ---- drain dQ_i (lane = query row): TMEM -> registers -> swizzled staging box -> TMA add-reduce
       mbar_wait(&dq_full[g], ph);
       tc_fence_after();
-      const int q = q0 + j;
-      float* dq_row = dq_bh + static_cast<long long>(q) * D;
+      uint32_t dq[D / 32][32];
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) tmem_ld32(tdP + 32 * c, dq[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&dq_free[g]);          // T_dP may be overwritten by dP(it+1)
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
-        uint32_t u[32];
-        tmem_ld32(tdP + 32 * c, u);
-        tmem_wait_ld();
-        if (c == D / 32 - 1) {
-          tc_fence_before();
-          mbar_arrive(&dq_free[g]);
-        }
-        if (q < p.N) {
+        if (issuer) tma_store_wait_read<0>();   // previous reduction has finished reading the staging box
+        named_bar_sync(1 + g, 128);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            red_add_v4(dq_row + 32 * c + 4 * i, __uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
-                       __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3]));
+        for (int u8 = 0; u8 < 8; ++u8)
+          *reinterpret_cast<uint4*>(stg_row + ((u8 ^ jx) << 4)) =
+              make_uint4(dq[c][4 * u8], dq[c][4 * u8 + 1], dq[c][4 * u8 + 2], dq[c][4 * u8 + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + g, 128);
+        if (issuer) {
+          tma_reduce_add_4d(&tmdQ, sStg + g * Cfg::STG_BYTES, 32 * c, q0, h, b);
+          tma_store_commit();
         }
       }
     }
+    if (issuer) tma_store_wait_all<0>();
 
     // ---- epilogue: group 0 stores dK (scaled), group 1 stores dV
     mbar_wait(dkv_done, 0);

@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(384, 1)
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<D>;
   constexpr int NSTAGE = Cfg::NSTAGE;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // align by offset (not by pointer cast) so the compiler keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                   // [2][TILE_BYTES]
   uint8_t* sKV = smem + 2 * Cfg::TILE_BYTES;            // [NSTAGE][TILE_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);

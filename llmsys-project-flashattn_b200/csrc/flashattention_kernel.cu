@@ -232,12 +232,13 @@ static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
 
 template <int D, bool CAUSAL>
 static int launch_bwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                         const CUtensorMap& tdo, const sm100::BwdParams& bp, cudaStream_t st) {
+                         const CUtensorMap& tdo, const CUtensorMap& tdq, const sm100::BwdParams& bp,
+                         cudaStream_t st) {
   using Cfg = sm100::BwdCfg<D>;
   auto kern = sm100::bwd_kernel<D, CAUSAL>;
   FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((a->N + 127) / 128, a->H, a->B);
-  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, bp);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdq, bp);
   fa::count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;
@@ -274,6 +275,11 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
     if ((rc = make_tmap(tm[i], src[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, a->H, a->N, a->d, s.sb, s.sh, s.sn, 64,
                         128)))
       return rc;
+  // fp32 dQ accumulator (contiguous B,H,N,d): [128 rows][32 columns] boxes for the TMA add-reduction
+  CUtensorMap tdq;
+  if ((rc = make_tmap(&tdq, acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->B, a->H, a->N, a->d,
+                      (long long)a->H * a->N * a->d, (long long)a->N * a->d, a->d, 32, 128)))
+    return rc;
   sm100::BwdParams bp;
   bp.B = a->B, bp.H = a->H, bp.N = a->N, bp.Npad = Npad;
   bp.kv_len = a->kv_len;
@@ -282,10 +288,10 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   bp.sb = s.sb, bp.sh = s.sh, bp.sn = s.sn;
   bp.scale = 1.0f / sqrtf((float)a->d);
   bp.scale_log2 = bp.scale * 1.4426950408889634f;
-  if (a->d == 128) rc = a->causal ? launch_bwd_tc<128, true>(a, tq, tk, tv, tdo, bp, st)
-                                  : launch_bwd_tc<128, false>(a, tq, tk, tv, tdo, bp, st);
-  else rc = a->causal ? launch_bwd_tc<64, true>(a, tq, tk, tv, tdo, bp, st)
-                      : launch_bwd_tc<64, false>(a, tq, tk, tv, tdo, bp, st);
+  if (a->d == 128) rc = a->causal ? launch_bwd_tc<128, true>(a, tq, tk, tv, tdo, tdq, bp, st)
+                                  : launch_bwd_tc<128, false>(a, tq, tk, tv, tdo, tdq, bp, st);
+  else rc = a->causal ? launch_bwd_tc<64, true>(a, tq, tk, tv, tdo, tdq, bp, st)
+                      : launch_bwd_tc<64, false>(a, tq, tk, tv, tdo, tdq, bp, st);
   if (rc) return rc;
   {
     const long long total8 = (long long)nacc / 8;
