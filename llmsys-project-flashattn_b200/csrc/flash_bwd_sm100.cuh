@@ -21,6 +21,7 @@
 //                     on B200, far too slow for 64 KB per tile pair)
 //   warp 8          : TMA producer (K,V once; Q_i + LSE_i + D_i 2-stage ring; dO_i single stage)
 //   warp 9          : tcgen05.mma issuer + TMEM allocation
+//   warp 10         : issues the dQ TMA reductions and recycles the two staging boxes
 // The tensor pipe executes in issue order, so single-buffered T_S / T_dP are enough: S^T(i+1)
 // is issued right after dV(i) and overlaps the other group's dS phase.
 // dQ is accumulated across KV-tile CTAs in fp32 (TMA add-reductions; summation order varies
@@ -189,7 +190,9 @@ __global__ void __launch_bounds__(384, 1)
   uint64_t* dq_full = bars + 17;     // [2]
   uint64_t* dq_free = bars + 19;     // [2]
   uint64_t* dkv_done = bars + 21;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* stg_full = bars + 22;    // [2 buffers]        staging box written by a compute group
+  uint64_t* stg_empty = bars + 24;   // [2 groups][2 buf]  staging box read by the TMA reduction
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -235,6 +238,9 @@ __global__ void __launch_bounds__(384, 1)
       mbar_init(&ds_empty[i], 1);
       mbar_init(&dq_full[i], 1);
       mbar_init(&dq_free[i], 128);
+      mbar_init(&stg_full[i], 128);
+      mbar_init(&stg_empty[i], 1);
+      mbar_init(&stg_empty[2 + i], 1);
     }
     fence_mbar_init();
   }
@@ -345,6 +351,35 @@ __global__ void __launch_bounds__(384, 1)
         mma_commit(dkv_done);
       }
       __syncwarp();
+    } else if (warp == 10) {
+      // ---------------------------------------------------------------- dQ reduction issuer
+      // Rounds (it, c): the compute group of iteration `it` fills staging buffer c&1 with columns
+      // [32c, 32c+32) of dQ_it; this thread turns each into one TMA add-reduction and hands the
+      // buffer back (to whichever group uses it two rounds later) once the TMA has read it.
+      if (lane == 0) {
+        constexpr int NR = D / 32;
+        int prev_g = 0, prev_b = 0;
+        bool have_prev = false;
+        for (int it = 0; it < n_iter; ++it) {
+          const int q0 = (q_first + it) * 128;
+          for (int c = 0; c < NR; ++c) {
+            const int bsel = c & 1;
+            mbar_wait(&stg_full[bsel], ((it * (NR / 2) + (c >> 1)) & 1));
+            tma_reduce_add_4d(&tmdQ, sStg + bsel * Cfg::STG_BYTES, 32 * c, q0, h, b);
+            tma_store_commit();
+            if (have_prev) {
+              tma_store_wait_read<1>();                       // the previous round's box has been read
+              mbar_arrive(&stg_empty[2 * prev_g + prev_b]);
+            }
+            // next user of this buffer: same iteration if c+2 < NR, otherwise the other group
+            prev_g = (c + 2 < NR) ? (it & 1) : ((it + 1) & 1);
+            prev_b = bsel;
+            have_prev = true;
+          }
+        }
+        tma_store_wait_all<0>();
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ compute groups
@@ -356,9 +391,8 @@ __global__ void __launch_bounds__(384, 1)
     const bool key_ok = (k0 + j) < kv_end;
     const bool all_keys_ok = (k0 + 128) <= kv_end;
     uint8_t* ds_row = sdS + j * 128;
-    uint8_t* stg_row = sStg + g * Cfg::STG_BYTES + j * 128;
+    uint8_t* stg_row = sStg + j * 128;
     const int jx = j & 7;
-    const bool issuer = (w == 0 && lane == 0);   // issues this group's TMA reductions
 
     for (int it = g; it < n_iter; it += 2) {
       const int ph = (it >> 1) & 1;
@@ -435,21 +469,18 @@ __global__ void __launch_bounds__(384, 1)
       mbar_arrive(&dq_free[g]);          // T_dP may be overwritten by dP(it+1)
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
-        if (issuer) tma_store_wait_read<0>();   // previous reduction has finished reading the staging box
-        named_bar_sync(1 + g, 128);
+        // use number u of buffer c&1 by THIS group; group 0's very first use finds the buffer free
+        const int u = (it >> 1) * (D / 64) + (c >> 1);
+        mbar_wait(&stg_empty[2 * g + (c & 1)], g == 0 ? ((u & 1) ^ 1) : (u & 1));
+        uint8_t* dst = stg_row + (c & 1) * Cfg::STG_BYTES;
 #pragma unroll
         for (int u8 = 0; u8 < 8; ++u8)
-          *reinterpret_cast<uint4*>(stg_row + ((u8 ^ jx) << 4)) =
+          *reinterpret_cast<uint4*>(dst + ((u8 ^ jx) << 4)) =
               make_uint4(dq[c][4 * u8], dq[c][4 * u8 + 1], dq[c][4 * u8 + 2], dq[c][4 * u8 + 3]);
         fence_proxy_async_smem();
-        named_bar_sync(1 + g, 128);
-        if (issuer) {
-          tma_reduce_add_4d(&tmdQ, sStg + g * Cfg::STG_BYTES, 32 * c, q0, h, b);
-          tma_store_commit();
-        }
+        mbar_arrive(&stg_full[c & 1]);
       }
     }
-    if (issuer) tma_store_wait_all<0>();
 
     // ---- epilogue: group 0 stores dK (scaled), group 1 stores dV
     mbar_wait(dkv_done, 0);
