@@ -42,7 +42,18 @@ struct BwdParams {
   void* dV;
   long long sb, sh, sn;
   float scale, scale_log2;
+  long long* trace;    // bring-up only (FA_TRACE builds): per-iteration clock64() stamps of one CTA
 };
+
+#ifdef FA_TRACE
+#define FA_TR(slot) \
+  if (tr && it < 48) tr[it * 32 + (slot)] = clock64();
+#define FA_TRW(slot) \
+  if (trw && it < 48) trw[it * 32 + 16 + 4 * w + (slot)] = clock64();
+#else
+#define FA_TR(slot)
+#define FA_TRW(slot)
+#endif
 
 template <int D>
 struct BwdCfg {
@@ -74,39 +85,49 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
-// D_i = sum_x dO*O and LSE_i (log2 domain) for the tensor-core backward; one warp per row,
-// rows padded to Npad per (b,h) with +inf / 0 so that out-of-range queries contribute P = 0.
-__global__ void bwd_prep_tc_kernel(int B, int H, int N, int Npad, int D, long long sb, long long sh, long long sn,
-                                   const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
-                                   const float* __restrict__ M, const float* __restrict__ L,
-                                   float* __restrict__ lse2, float* __restrict__ dvec) {
+// Pre-pass of the tensor-core backward: D_i = sum_x dO*O and LSE_i (log2 domain), rows padded to
+// Npad per (b,h) with +inf / 0 so that out-of-range queries contribute P = 0; the same kernel
+// zero-fills the fp32 dQ accumulator (saves a separate memset pass).  16 lanes x 16 bytes cover one
+// 128-element row, so every load is a full 128-bit coalesced access.
+template <int D>
+__global__ void __launch_bounds__(256)
+    bwd_prep_tc_kernel(int B, int H, int N, int Npad, long long sb, long long sh, long long sn,
+                       const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                       const float* __restrict__ M, const float* __restrict__ L, float* __restrict__ lse2,
+                       float* __restrict__ dvec, float4* __restrict__ dq_acc4, long long n_acc4) {
+  constexpr int LPR = D / 8;  // lanes per row (8 bf16 = 16 bytes each)
   const long long rows = static_cast<long long>(B) * H * Npad;
-  const int lane = threadIdx.x & 31;
-  for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
-       r += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid; i < n_acc4; i += nthreads) dq_acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int sub = threadIdx.x % LPR;
+  for (long long r = tid / LPR; r < rows; r += nthreads / LPR) {
     const int n = static_cast<int>(r % Npad);
     const long long bh = r / Npad;
-    if (n >= N) {
-      if (lane == 0) {
+    float s = 0.f;
+    if (n < N) {
+      const long long off = (bh / H) * sb + (bh % H) * sh + static_cast<long long>(n) * sn + sub * 8;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(O + off));
+      const uint4 c = __ldg(reinterpret_cast<const uint4*>(dO + off));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s = fmaf(__uint_as_float(aw[k] << 16), __uint_as_float(cw[k] << 16), s);
+        s = fmaf(__uint_as_float(aw[k] & 0xffff0000u), __uint_as_float(cw[k] & 0xffff0000u), s);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (sub == 0) {
+      if (n < N) {
+        const long long sr = bh * N + n;
+        const float l = L[sr];
+        lse2[r] = (l > 0.f) ? (M[sr] + logf(l)) * 1.4426950408889634f : INFINITY;
+        dvec[r] = s;
+      } else {
         lse2[r] = INFINITY;
         dvec[r] = 0.f;
       }
-      continue;
-    }
-    const long long off = (bh / H) * sb + (bh % H) * sh + static_cast<long long>(n) * sn;
-    float s = 0.f;
-    for (int x = lane * 2; x < D; x += 64) {
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(O + off + x);
-      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dO + off + x);
-      s += __bfloat162float(a.x) * __bfloat162float(b.x) + __bfloat162float(a.y) * __bfloat162float(b.y);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      const long long sr = bh * N + n;
-      const float l = L[sr];
-      lse2[r] = (l > 0.f) ? (M[sr] + logf(l)) * 1.4426950408889634f : INFINITY;
-      dvec[r] = s;
     }
   }
 }
@@ -197,6 +218,9 @@ __global__ void __launch_bounds__(384, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = kt * 128;
+#ifdef FA_TRACE
+  long long* tr = (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace : nullptr;
+#endif
   int kv_end = p.N;
   if (p.kv_len) kv_end = min(kv_end, max(__ldg(p.kv_len + b), 0));
   const int nq = (p.N + 127) >> 7;
@@ -312,20 +336,25 @@ __global__ void __launch_bounds__(384, 1)
           // dV += P^T dO_i : A = P^T in TMEM (bf16, 8 columns per 16 queries), B = dO_i as [K=q][N=d]
           mbar_wait(&p_full[s], ph);
           tc_fence_after();
+          FA_TR(0)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             mma_ts(tdV, tS + k * 8, make_smem_desc(adO + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn,
                    (it > 0 || k > 0) ? 1u : 0u);
           mma_commit(do_empty);   // dO_i is dead once dV(i) has run (dP(i) ran earlier)
+          FA_TR(1)
           if (it + 1 < n_iter) {
             const int s1 = (it + 1) & 1;
             mbar_wait(&q_full[s1], ((it + 1) >> 1) & 1);
             tc_fence_after();
+            FA_TR(2)
             issue_nt(tS, aK, smem_u32(sQ + s1 * Cfg::TILE_BYTES));
             mma_commit(&s_full[s1]);
+            FA_TR(3)
           }
           mbar_wait(&ds_full[s], ph);
           tc_fence_after();
+          FA_TR(4)
           // dQ_i = dS K : A = dS^T tile read MN-major ([K=key][M=q]), B = K tile as [K=key][N=d]
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -339,13 +368,16 @@ __global__ void __launch_bounds__(384, 1)
                    make_smem_desc(aQ + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
           mma_commit(&ds_empty[s]);
           mma_commit(&q_empty[s]);
+          FA_TR(5)
           if (it + 1 < n_iter) {
             const int s1 = (it + 1) & 1;
             mbar_wait(do_full, (it + 1) & 1);
             mbar_wait(&dq_free[s], ph);
             tc_fence_after();
+            FA_TR(6)
             issue_nt(tdP, aV, adO);
             mma_commit(&dp_full[s1]);
+            FA_TR(7)
           }
         }
         mma_commit(dkv_done);
@@ -393,6 +425,10 @@ __global__ void __launch_bounds__(384, 1)
     uint8_t* ds_row = sdS + j * 128;
     uint8_t* stg_row = sStg + j * 128;
     const int jx = j & 7;
+#ifdef FA_TRACE
+    long long* trw = tr;   // lane 0 of every warp of the group
+    if (w != 0) tr = nullptr;
+#endif
 
     for (int it = g; it < n_iter; it += 2) {
       const int ph = (it >> 1) & 1;
@@ -402,6 +438,8 @@ __global__ void __launch_bounds__(384, 1)
       // ---- P^T = exp2(S^T * scale*log2e - LSE2[q])
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
+      FA_TR(8)
+      FA_TRW(2)
       float s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -411,6 +449,7 @@ __global__ void __launch_bounds__(384, 1)
         for (int i = 0; i < 32; ++i) s[32 * c + i] = __uint_as_float(u[i]);
       }
       tmem_wait_ld();
+      FA_TR(9)
       mbar_wait(&q_full[g], ph);  // LSE / D vectors of this Q tile are in shared memory
       uint32_t pk[64];
       const bool diag = CAUSAL && (q0 < k0 + 128);
@@ -427,17 +466,23 @@ __global__ void __launch_bounds__(384, 1)
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
+      FA_TR(10)
+      FA_TRW(0)
 
       // ---- dS^T = P^T * (dP^T - D[q])  -> shared memory (bf16, 128B-swizzled rows)
       mbar_wait(&dp_full[g], ph);
       tc_fence_after();
+      FA_TR(11)
+      FA_TRW(3)
       if (it >= 1) mbar_wait(&ds_empty[g ^ 1], ((it - 1) >> 1) & 1);  // dK(it-1) done with the buffer
+      uint32_t ua[2][32];
+      tmem_ld32(tdP, ua[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t u[32];
-        tmem_ld32(tdP + 32 * c, u);
-        tmem_wait_ld();
+        tmem_wait_ld();                                         // chunk c is in registers
+        if (c < 3) tmem_ld32(tdP + 32 * (c + 1), ua[(c + 1) & 1]);  // prefetch the next 32 columns
         if (c == 3) tc_fence_before();
+        const uint32_t(&u)[32] = ua[c & 1];
 #pragma unroll
         for (int v8 = 0; v8 < 4; ++v8) {   // 8 queries -> one 16-byte piece
           const float4 da = *reinterpret_cast<const float4*>(dv + 32 * c + 8 * v8);
@@ -457,16 +502,20 @@ __global__ void __launch_bounds__(384, 1)
       }
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[g]);
+      FA_TR(12)
+      FA_TRW(1)
 
       // ---- drain dQ_i (lane = query row): TMEM -> registers -> swizzled staging box -> TMA add-reduce
       mbar_wait(&dq_full[g], ph);
       tc_fence_after();
+      FA_TR(13)
       uint32_t dq[D / 32][32];
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) tmem_ld32(tdP + 32 * c, dq[c]);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&dq_free[g]);          // T_dP may be overwritten by dP(it+1)
+      FA_TR(14)
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         // use number u of buffer c&1 by THIS group; group 0's very first use finds the buffer free
@@ -480,6 +529,7 @@ __global__ void __launch_bounds__(384, 1)
         fence_proxy_async_smem();
         mbar_arrive(&stg_full[c & 1]);
       }
+      FA_TR(15)
     }
 
     // ---- epilogue: group 0 stores dK (scaled), group 1 stores dV

@@ -276,9 +276,16 @@ __global__ void __launch_bounds__(384, 1)
           for (int i = 0; i < 128; ++i)
             if (i >= limit) s[i] = -INFINITY;
         }
-        float mx = s[0];
+        // four independent max chains (a single 128-long dependent chain costs ~500 clk of latency)
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-        for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+        for (int i = 4; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, s[i]);
+          mx1 = fmaxf(mx1, s[i + 1]);
+          mx2 = fmaxf(mx2, s[i + 2]);
+          mx3 = fmaxf(mx3, s[i + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         m_true = fmaxf(m_true, mx);
         if (j == 0) {
           m_used = (mx == -INFINITY) ? 0.f : mx;
@@ -304,13 +311,16 @@ __global__ void __launch_bounds__(384, 1)
           }
         }
         const float neg_m = -m_used * sc;
-        float rs = 0.f;
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 128; i += 4) {
           s[i] = ex2_approx(fmaf(s[i], sc, neg_m));
-          rs += s[i];
+          s[i + 1] = ex2_approx(fmaf(s[i + 1], sc, neg_m));
+          s[i + 2] = ex2_approx(fmaf(s[i + 2], sc, neg_m));
+          s[i + 3] = ex2_approx(fmaf(s[i + 3], sc, neg_m));
+          rs0 += s[i], rs1 += s[i + 1], rs2 += s[i + 2], rs3 += s[i + 3];
         }
-        l_run += rs;
+        l_run += (rs0 + rs1) + (rs2 + rs3);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[32];

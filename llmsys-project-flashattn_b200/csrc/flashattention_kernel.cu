@@ -19,6 +19,7 @@
 namespace fa {
 
 static int g_mode = -1;  // resolved lazily from MINITORCH_FA_MODE
+static long long* g_trace = nullptr;  // FA_TRACE bring-up builds only
 
 static int current_mode() {
   if (g_mode < 0) {
@@ -257,13 +258,17 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   float* acc = static_cast<float*>(g_pool.get(14, sizeof(float) * nacc));
   if (!ws || !acc) return set_error(FA_ERR_CUDA, "flash bwd: workspace allocation failed");
   float *lse2 = ws, *dvec = ws + rows_pad;
-  FA_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(float) * nacc, st));
   {
-    long long blocks = ((long long)rows_pad + 7) / 8;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    sm100::bwd_prep_tc_kernel<<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, a->d, s.sb, s.sh, s.sn,
-                                                           (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, m, l,
-                                                           lse2, dvec);
+    const long long blocks = 148 * 8;
+    const long long n_acc4 = (long long)(nacc / 4);
+    if (a->d == 128)
+      sm100::bwd_prep_tc_kernel<128><<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, s.sb, s.sh, s.sn,
+                                                                 (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, m,
+                                                                 l, lse2, dvec, (float4*)acc, n_acc4);
+    else
+      sm100::bwd_prep_tc_kernel<64><<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, s.sb, s.sh, s.sn,
+                                                                (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, m,
+                                                                l, lse2, dvec, (float4*)acc, n_acc4);
     fa::count_launch();
     FA_CUDA_CHECK(cudaGetLastError());
   }
@@ -288,6 +293,7 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   bp.sb = s.sb, bp.sh = s.sh, bp.sn = s.sn;
   bp.scale = 1.0f / sqrtf((float)a->d);
   bp.scale_log2 = bp.scale * 1.4426950408889634f;
+  bp.trace = g_trace;
   if (a->d == 128) rc = a->causal ? launch_bwd_tc<128, true>(a, tq, tk, tv, tdo, tdq, bp, st)
                                   : launch_bwd_tc<128, false>(a, tq, tk, tv, tdo, tdq, bp, st);
   else rc = a->causal ? launch_bwd_tc<64, true>(a, tq, tk, tv, tdo, tdq, bp, st)
@@ -354,6 +360,9 @@ void fa_set_mode(int mode) {
   g_mode = (mode == FA_MODE_BF16) ? FA_MODE_BF16 : FA_MODE_FP32;
 }
 int fa_get_mode(void) { return current_mode(); }
+#ifdef FA_TRACE
+void fa_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+#endif
 
 int fa_cast_f32_to_bf16_dev(const float* src, void* dst, size_t n, fa_stream_t stream) {
   clear_error();
