@@ -2,20 +2,20 @@
 //
 // One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong so the
 // tensor pipe works on one tile while the other tile's softmax runs on the CUDA cores.
-//   warps 0-3 : softmax group 0 (thread t of warp w owns query row 32w+t of Q tile 0)
-//   warps 4-7 : softmax group 1 (Q tile 1)
-//   warp  8   : TMA producer (Q tiles once; K,V tiles through an NSTAGE ring)
-//   warp  9   : tcgen05.mma issuer (one lane) + TMEM allocation
-//   warps 10-11: idle (they complete the third warpgroup so setmaxnreg can move its registers
-//               to the softmax groups: 208 regs/thread there, 88 here; the total must stay
-//               within the 168 x 384 registers the CTA was launched with)
+//   warps 0-15 : four softmax groups.  Group (g, hh) = Q tile g, column half hh: thread t of warp w
+//                owns query row 32w+t of tile g (= its TMEM lane) and 2 x 32 of the 128 score columns.
+//                Two threads per row give every SM sub-partition four softmax warps to interleave
+//                (with one thread per row the phase was latency-bound at ~5 clk per instruction);
+//                the two halves agree on the row max through a 4 KB shared-memory exchange.
+//   warp 16    : TMA producer (Q tiles once; K,V tiles through an NSTAGE ring)
+//   warp 17    : tcgen05.mma issuer (one lane) + TMEM allocation
+//   (18 warps = 576 threads -> 112 registers per thread without any setmaxnreg juggling)
 // TMEM (512 columns): S0 | S1 (128 fp32 columns each), O0 | O1 (D columns each).  P (bf16)
 // overwrites the first 64 columns of its S tile and is consumed directly from TMEM as the
 // A operand of the PV MMA, so P never touches shared memory.
 // Per KV tile j and Q tile g the issuer runs   O_g += P_g(j) V_j ;  S_g = Q_g K_{j+1}^T
-// and the softmax group g turns S_g into P_g: row max, lazy rescale of O_g (only when the max
+// and the softmax groups of g turn S_g into P_g: row max, lazy rescale of O_g (only when the max
 // grew by more than 2^8), exp2 with the 1/sqrt(d)*log2(e) scale folded into one FFMA, row sum.
-// One thread owns one row, so the row reductions need no cross-thread traffic at all.
 // Masks: causal (tiles above the diagonal are skipped, only the diagonal tile is masked),
 // key padding as kv_len[b] (tiles beyond it are skipped) or a generic additive (B,N) mask.
 #pragma once
@@ -34,18 +34,27 @@ struct FwdParams {
   float* L;               // (B,H,N) sum exp(s - m)
   float scale;            // 1/sqrt(d)
   float scale_log2;       // scale * log2(e)
+  long long* trace;       // bring-up only (FA_TRACE builds)
 };
+
+#ifdef FA_TRACE
+#define FA_FTR(slot) \
+  if (tr && j < 48) tr[j * 32 + (slot)] = clock64();
+#else
+#define FA_FTR(slot)
+#endif
 
 template <int D>
 struct FwdCfg {
   static constexpr int NCHUNK = D / 64;            // 128-byte swizzle chunks per row
   static constexpr int CHUNK_BYTES = 128 * 128;    // [128 rows][64 bf16]
   static constexpr int TILE_BYTES = NCHUNK * CHUNK_BYTES;
-  static constexpr int NSTAGE = (D == 128) ? 5 : 8;
+  static constexpr int NSTAGE = (D == 128) ? 4 : 8;
   static constexpr int SMEM_TILES = 2 * TILE_BYTES + NSTAGE * TILE_BYTES;
-  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [parity][tile][half][row] fp32 row-max / row-sum exchange
+  static constexpr int SMEM_BYTES = SMEM_TILES + XCHG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
-  static constexpr int NTHREADS = 384;
+  static constexpr int NTHREADS = 576;
 };
 
 __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* r) {
@@ -76,19 +85,25 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
   }
 }
 
+#ifndef FA_FWD_EMU
+#define FA_FWD_EMU 0   // exponentials per 8 evaluated on the FMA pipe instead of MUFU (measured on B200:
+                       // 0 -> 1.53 ms, 2 -> 1.62 ms, 3 -> 1.75 ms at cfg4: the FP32 pipe is the busier one, so off)
+#endif
 // MASKMODE: 0 none (N-ragged only), 1 kv_len[b], 2 additive key mask (B,N)
 template <int D, bool CAUSAL, int MASKMODE, typename OutT>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(576, 1)
     fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<D>;
   constexpr int NSTAGE = Cfg::NSTAGE;
+  constexpr int EMU = FA_FWD_EMU;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align by offset (not by pointer cast) so the compiler keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                   // [2][TILE_BYTES]
   uint8_t* sKV = smem + 2 * Cfg::TILE_BYTES;            // [NSTAGE][TILE_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);
+  float* xchg = reinterpret_cast<float*>(smem + Cfg::SMEM_TILES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES + Cfg::XCHG_BYTES);
   uint64_t* q_full = bars;                 // [2]
   uint64_t* kv_full = bars + 2;            // [NSTAGE]
   uint64_t* kv_empty = kv_full + NSTAGE;   // [NSTAGE]
@@ -98,6 +113,9 @@ __global__ void __launch_bounds__(384, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FA_TRACE
+  long long* tr = (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace : nullptr;
+#endif
   const int qb = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // causal: longest blocks first
   const int h = blockIdx.y, b = blockIdx.z;
   int kv_end = p.N;
@@ -111,14 +129,14 @@ __global__ void __launch_bounds__(384, 1)
   }
   const int nk = max(nkv[0], nkv[1]);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
       mbar_init(&o_done[i], 1);
     }
     for (int i = 0; i < NSTAGE; ++i) {
@@ -127,15 +145,14 @@ __global__ void __launch_bounds__(384, 1)
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
-   reg_dealloc<88>();
-   if (warp == 8) {
+  if (warp >= 16) {
+   if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
 #pragma unroll
@@ -159,7 +176,7 @@ __global__ void __launch_bounds__(384, 1)
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && nk > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
@@ -209,15 +226,19 @@ __global__ void __launch_bounds__(384, 1)
           if (j < nkv[g]) {
             mbar_wait(&p_full[g], j & 1);
             tc_fence_after();
+            FA_FTR(0 + 4 * g)
             issue_pv(g, tv, j > 0);
             mma_commit(&o_done[g]);
+            FA_FTR(1 + 4 * g)
             if (j + 1 < nkv[g]) {
               if (!k_ready) {
                 wait_full(tk);
                 k_ready = true;
               }
+              FA_FTR(2 + 4 * g)
               issue_qk(g, tk);
               mma_commit(&s_full[g]);
+              FA_FTR(3 + 4 * g)
             }
           }
         }
@@ -226,20 +247,30 @@ __global__ void __launch_bounds__(384, 1)
       }
     }
     __syncwarp();
-   }  // warps 10, 11 idle
+   }
   } else {
     // ------------------------------------------------------------------ softmax groups
-    reg_alloc<208>();
-    const int g = warp >> 2, w = warp & 3;
-    const int row = r0[g] + w * 32 + lane;
+    const int wg = warp >> 2, w = warp & 3;
+    const int g = wg & 1, hh = wg >> 1;          // Q tile, column half
+    const int rl = w * 32 + lane;                // row inside the tile == TMEM lane
+    const int row = r0[g] + rl;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
-    const uint32_t tS = lane_base + (g ? Cfg::S_COL1 : Cfg::S_COL0);
-    const uint32_t tO = lane_base + (g ? Cfg::O_COL1 : Cfg::O_COL0);
+    const uint32_t tSg = lane_base + (g ? Cfg::S_COL1 : Cfg::S_COL0);
+    // A thread owns 2 x 32 score columns of its row: chunk A = keys [32hh, 32hh+32) (columns the
+    // packed P will overwrite) and chunk B = keys [64+32hh, 96+32hh) (columns nobody overwrites before
+    // the next QK^T, so chunk B can be dropped after the max pass and re-read for the exp pass: only
+    // 32 scores are ever live in registers).
+    const uint32_t tA = tSg + 32 * hh, tB = tSg + 64 + 32 * hh;
+    const uint32_t tPA = tSg + 16 * hh, tPB = tSg + 32 + 16 * hh;   // packed P columns of chunk A / B
+    const uint32_t tO = lane_base + (g ? Cfg::O_COL1 : Cfg::O_COL0) + (D / 2) * hh;
     const float sc = (MASKMODE == 2) ? 1.0f : p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
     const float* mrow = (MASKMODE == 2) ? p.key_mask + static_cast<long long>(b) * p.N : nullptr;
-    OutT* orow = reinterpret_cast<OutT*>(p.O) + b * p.o_sb + h * p.o_sh + static_cast<long long>(row) * p.o_sn;
+    OutT* orow = reinterpret_cast<OutT*>(p.O) + b * p.o_sb + h * p.o_sh + static_cast<long long>(row) * p.o_sn +
+                 (D / 2) * hh;
     const long long stat_idx = (static_cast<long long>(b) * p.H + h) * p.N + row;
+    float* x_mine = xchg + (g * 2 + hh) * 128 + rl;        // + parity * 512
+    float* x_peer = xchg + (g * 2 + (hh ^ 1)) * 128 + rl;
 
     if (nkv[g] == 0) {
       if (row < p.N) {  // no visible key at all (kv_len == 0): O = 0, m = -inf, l = 0
@@ -247,50 +278,86 @@ __global__ void __launch_bounds__(384, 1)
 #pragma unroll
         for (int i = 0; i < 32; ++i) z[i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) store_row32<OutT>(orow + 32 * c, z);
-        p.M[stat_idx] = -INFINITY;
-        p.L[stat_idx] = 0.f;
+        for (int c = 0; c < D / 64; ++c) store_row32<OutT>(orow + 32 * c, z);
+        if (hh == 0) {
+          p.M[stat_idx] = -INFINITY;
+          p.L[stat_idx] = 0.f;
+        }
       }
     } else {
       float m_used = -INFINITY, m_true = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < nkv[g]; ++j) {
-        mbar_wait(&s_full[g], j & 1);
-        tc_fence_after();
-        float s[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32f(tS + 32 * c, &s[32 * c]);
+      // 32 scores of my row starting at key `key0` -> registers, masks applied
+      auto load_chunk = [&](uint32_t taddr, int key0, float(&s)[32]) {
+        tmem_ld32f(taddr, s);
         tmem_wait_ld();
-        const int k0 = j * 128;
         if (MASKMODE == 2) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i) {
-            const float mv = (k0 + i < p.N) ? __ldg(mrow + k0 + i) : 0.f;
+          for (int i = 0; i < 32; ++i) {
+            const float mv = (key0 + i < p.N) ? __ldg(mrow + key0 + i) : 0.f;
             s[i] = fmaf(s[i], p.scale_log2, mv * LOG2E);
           }
         }
-        const bool need_mask = (k0 + 128 > kv_end) || (CAUSAL && (k0 + 127 > r0[g]));
-        if (need_mask) {
-          int limit = kv_end - k0;
-          if (CAUSAL) limit = min(limit, row - k0 + 1);
+        if ((key0 + 32 > kv_end) || (CAUSAL && (key0 + 31 > r0[g]))) {
+          int limit = kv_end - key0;
+          if (CAUSAL) limit = min(limit, row - key0 + 1);
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
+          for (int i = 0; i < 32; ++i)
             if (i >= limit) s[i] = -INFINITY;
         }
-        // four independent max chains (a single 128-long dependent chain costs ~500 clk of latency)
-        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      };
+      auto max32 = [](const float(&s)[32]) {
+        float a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3];
 #pragma unroll
-        for (int i = 4; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, s[i]);
-          mx1 = fmaxf(mx1, s[i + 1]);
-          mx2 = fmaxf(mx2, s[i + 2]);
-          mx3 = fmaxf(mx3, s[i + 3]);
+        for (int i = 4; i < 32; i += 4) {
+          a0 = fmaxf(a0, s[i]), a1 = fmaxf(a1, s[i + 1]), a2 = fmaxf(a2, s[i + 2]), a3 = fmaxf(a3, s[i + 3]);
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+      };
+      // exp2 of 32 scores -> 16 packed bf16x2 registers, returns their sum.  Of every 8 exponentials
+      // EMU are evaluated by ex2_poly on the FMA pipe, the rest by MUFU.EX2 (see ptx.cuh).
+      auto exp_pack = [&](const float(&s)[32], float neg_m, uint32_t(&pk)[16]) {
+        float r0_ = 0.f, r1_ = 0.f, r2_ = 0.f, r3_ = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float e[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float x = fmaf(s[i + t], sc, neg_m);
+            const bool emu = (EMU >= 1 && t == 7) || (EMU >= 2 && t == 3) || (EMU >= 3 && t == 5) ||
+                             (EMU >= 4 && t == 1);
+            e[t] = emu ? ex2_poly(x) : ex2_approx(x);
+          }
+          r0_ += e[0] + e[4], r1_ += e[1] + e[5], r2_ += e[2] + e[6], r3_ += e[3] + e[7];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) pk[i / 2 + t] = pack_bf16x2(e[2 * t], e[2 * t + 1]);
+        }
+        return (r0_ + r1_) + (r2_ + r3_);
+      };
+      for (int j = 0; j < nkv[g]; ++j) {
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        FA_FTR(8 + 4 * wg)
+        const int kA = j * 128 + 32 * hh, kB = kA + 64;
+        float mx;
+        {
+          float sB[32];
+          load_chunk(tB, kB, sB);
+          mx = max32(sB);
+        }
+        float sA[32];
+        load_chunk(tA, kA, sA);
+        mx = fmaxf(mx, max32(sA));
+        x_mine[(j & 1) * 512] = mx;
+        FA_FTR(9 + 4 * wg)
+        named_bar_sync(1 + g, 256);   // both halves hold their chunk A (P may overwrite it) and published
+        FA_FTR(10 + 4 * wg)
+        mx = fmaxf(mx, x_peer[(j & 1) * 512]);
         m_true = fmaxf(m_true, mx);
         if (j == 0) {
           m_used = (mx == -INFINITY) ? 0.f : mx;
         } else {
-          // lazy rescale: only when some row of this warp grew by more than 2^8
+          // lazy rescale: only when some row of this warp grew by more than 2^8.  The partner warp of
+          // the other half sees the same 32 row maxima, so both take the same decision.
           const bool want = (mx - m_used) * sc > 8.0f;
           if (__any_sync(0xffffffffu, want)) {
             const float m_new = fmaxf(m_used, mx);
@@ -299,45 +366,42 @@ __global__ void __launch_bounds__(384, 1)
             l_run *= factor;
             mbar_wait(&o_done[g], (j - 1) & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
-              uint32_t u[32];
-              tmem_ld32(tO + 32 * c, u);
+#pragma unroll 1
+            for (int c = 0; c < D / 16; ++c) {   // my half of the O columns, 8 at a time (rare path)
+              uint32_t u[8];
+              tmem_ld8(tO + 8 * c, u);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * factor);
-              tmem_st32(tO + 32 * c, u);
+              for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * factor);
+              tmem_st8(tO + 8 * c, u);
             }
           }
         }
         const float neg_m = -m_used * sc;
-        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          s[i] = ex2_approx(fmaf(s[i], sc, neg_m));
-          s[i + 1] = ex2_approx(fmaf(s[i + 1], sc, neg_m));
-          s[i + 2] = ex2_approx(fmaf(s[i + 2], sc, neg_m));
-          s[i + 3] = ex2_approx(fmaf(s[i + 3], sc, neg_m));
-          rs0 += s[i], rs1 += s[i + 1], rs2 += s[i + 2], rs3 += s[i + 3];
+        uint32_t pk[16];
+        l_run += exp_pack(sA, neg_m, pk);
+        tmem_st16(tPA, pk);
+        {
+          float sB[32];
+          load_chunk(tB, kB, sB);   // re-read: cheaper than keeping 32 more registers live
+          l_run += exp_pack(sB, neg_m, pk);
         }
-        l_run += (rs0 + rs1) + (rs2 + rs3);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[64 * c + 2 * i], s[64 * c + 2 * i + 1]);
-          tmem_st32(tS + 32 * c, pk);
-        }
+        tmem_st16(tPB, pk);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&p_full[g]);
+        FA_FTR(11 + 4 * wg)
       }
-      // epilogue: O / l -> global, statistics
+      // epilogue: combine the two halves' row sums, O / l -> global, statistics
+      const int par = nkv[g] & 1;
+      x_mine[par * 512] = l_run;
+      named_bar_sync(1 + g, 256);
+      const float l_tot = l_run + x_peer[par * 512];
       mbar_wait(&o_done[g], (nkv[g] - 1) & 1);
       tc_fence_after();
-      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      const float inv = (l_tot > 0.f) ? 1.0f / l_tot : 0.f;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < D / 64; ++c) {
         float o[32];
         tmem_ld32f(tO + 32 * c, o);
         tmem_wait_ld();
@@ -345,16 +409,16 @@ __global__ void __launch_bounds__(384, 1)
         for (int i = 0; i < 32; ++i) o[i] *= inv;
         if (row < p.N) store_row32<OutT>(orow + 32 * c, o);
       }
-      if (row < p.N) {
+      if (row < p.N && hh == 0) {
         const float m_out = (MASKMODE == 2) ? m_true * (1.0f / LOG2E) : m_true * p.scale;
         p.M[stat_idx] = m_out;
-        p.L[stat_idx] = (m_true == -INFINITY) ? 0.f : l_run * ex2_approx((m_used - m_true) * sc);
+        p.L[stat_idx] = (m_true == -INFINITY) ? 0.f : l_tot * ex2_approx((m_used - m_true) * sc);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace sm100

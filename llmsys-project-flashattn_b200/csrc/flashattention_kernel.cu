@@ -221,6 +221,7 @@ static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   fp.M = m, fp.L = l;
   fp.scale = 1.0f / sqrtf((float)a->d);
   fp.scale_log2 = fp.scale * 1.4426950408889634f;
+  fp.trace = g_trace;
   const int maskmode = a->key_mask ? 2 : (a->kv_len ? 1 : 0);
 #define FA_FWD_CASE(DD, CC, MM) \
   if (a->d == DD && (a->causal != 0) == CC && maskmode == MM) return launch_fwd_tc<DD, CC, MM, OutT>(a, tq, tk, tv, fp, st);
