@@ -13,6 +13,9 @@ for g in $groups; do
     diag_fwd) run diag_fwd python tools/diag_fwd.py ;;
     diag_bwd) run diag_bwd python tools/diag_bwd.py ;;
     flash_bf16) run flash_bf16 python -m pytest tests/test_gpu_flash_bf16.py -q -m gpu ;;
+    mha) run mha python -m pytest tests/test_gpu_mha_integration.py -q -m gpu ;;
+    extra) run extra python tools/bench_extra.py --out gpurun_out/extra.json ;;
+    alltests) run alltests python -m pytest tests -x -q -m gpu ;;
     bench) run bench python bench.py --steps 10 --warmup 3 ;;
     benchq) run benchq python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu ;;
     smoke) run smoke python -c "import __graft_entry__ as g; g.smoke()" ;;
