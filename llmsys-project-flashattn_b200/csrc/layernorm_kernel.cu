@@ -8,6 +8,7 @@
 //   backward: x and dy read once, dx written once; dgamma/dbeta are accumulated in registers
 //             across the rows a CTA owns and reduced through a tiny [grid][h] workspace
 //             -> 12 B/elem (the reference reads x and dy twice: 20 B/elem)
+// Wide rows (2048..4096) in the backward are staged through shared memory with cp.async.bulk.
 // Semantics kept from the reference: `vars` stores var + 1e-8 (:70) and the backward adds
 // 1e-8 again (:229, :310); hidden_dim % 4 == 0 is required (:105); the 4096 cap of the
 // backward (:411) is lifted to 16384.
@@ -222,19 +223,182 @@ __global__ void __launch_bounds__(BLOCK) layernorm_bw_kernel(float* __restrict__
   }
 }
 
-// dgamma[c] = sum_p part_g[p][c]; one thread per column, coalesced along h.
-__global__ void ln_bw_reduce_kernel(float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    const float* __restrict__ part_g, const float* __restrict__ part_b,
-                                    int nparts, int h) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= h) return;
+// dgamma[c] = sum_p part_g[p][c].  32x32 threads per CTA: threadIdx.x walks 32 consecutive columns
+// (coalesced 128-byte rows of the partial matrix), threadIdx.y strides over the partial rows, then a
+// shared-memory transpose + warp shuffle folds the 32 row-strides.  (One thread per column with a
+// serial loop over ~300 partial rows was latency-bound and cost as much as the main kernel.)
+__global__ void __launch_bounds__(1024) ln_bw_reduce_kernel(float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            const float* __restrict__ part_g,
+                                                            const float* __restrict__ part_b, int nparts, int h) {
+  __shared__ float sg[32][33], sb[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float g = 0.f, b = 0.f;
-  for (int p = 0; p < nparts; ++p) {
-    g += part_g[static_cast<size_t>(p) * h + c];
-    b += part_b[static_cast<size_t>(p) * h + c];
+  if (c < h) {
+    for (int p = threadIdx.y; p < nparts; p += 32) {
+      g += __ldg(part_g + static_cast<size_t>(p) * h + c);
+      b += __ldg(part_b + static_cast<size_t>(p) * h + c);
+    }
   }
-  dgamma[c] = g;
-  dbeta[c] = b;
+  sg[threadIdx.y][threadIdx.x] = g;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  g = sg[threadIdx.x][threadIdx.y];   // transpose: lanes now hold the 32 row-strides of column threadIdx.y
+  b = sb[threadIdx.x][threadIdx.y];
+  g = warp_sum(g);
+  b = warp_sum(b);
+  const int co = blockIdx.x * 32 + threadIdx.y;
+  if (threadIdx.x == 0 && co < h) {
+    dgamma[co] = g;
+    dbeta[co] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward for wide rows (2048 <= hidden <= 4096): rows are staged through shared memory by bulk
+// async copies (cp.async.bulk, the 1-D TMA path) issued by a producer warp several rows ahead, so
+// HBM latency never sits in front of the per-row reductions.  Two persistent CTAs per SM: 8 compute
+// warps (a row = 256 threads x ITERS float4) + 1 producer warp; a stage = one x row + one dy row.
+// The compute threads copy their slice of the stage into registers and release it at once.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(ln_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int ITERS>
+__global__ void __launch_bounds__(288, 2)
+    layernorm_bw_staged_kernel(float* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b,
+                               const float* __restrict__ dy, const float* __restrict__ x,
+                               const float* __restrict__ gamma, const float* __restrict__ vars,
+                               const float* __restrict__ means, long long rows, int h, int nstage) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ uint64_t full[8], empty[8];
+  __shared__ float2 red2[8];
+  const int h4 = h >> 2;
+  const size_t row_bytes = static_cast<size_t>(h) * 4;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const float inv_h = 1.0f / static_cast<float>(h);
+  if (t == 0) {
+    for (int i = 0; i < nstage; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ln_smem_u32(&full[i])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ln_smem_u32(&empty[i])), "r"(256) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long nmine = (rows > first) ? (rows - first + stride - 1) / stride : 0;
+
+  if (warp == 8) {
+    // ---- producer: one lane streams this CTA's rows into the stage ring
+    if (lane == 0) {
+      for (long long i = 0; i < nmine; ++i) {
+        const int st = static_cast<int>(i % nstage);
+        const uint32_t ph = static_cast<uint32_t>((i / nstage) & 1);
+        ln_mbar_wait(&empty[st], ph ^ 1);
+        const long long row = first + i * stride;
+        uint8_t* dst = ln_smem + static_cast<size_t>(st) * 2 * row_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ln_smem_u32(&full[st])),
+                     "r"(static_cast<uint32_t>(2 * row_bytes))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ln_smem_u32(dst)),
+                     "l"(x + row * h), "r"(static_cast<uint32_t>(row_bytes)), "r"(ln_smem_u32(&full[st]))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ln_smem_u32(dst + row_bytes)),
+                     "l"(dy + row * h), "r"(static_cast<uint32_t>(row_bytes)), "r"(ln_smem_u32(&full[st]))
+                     : "memory");
+      }
+    }
+    return;
+  }
+
+  // ---- compute warps
+  float4 acc_g[ITERS], acc_b[ITERS], g4[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int c = it * 256 + t;
+    acc_g[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g4[it] = (c < h4) ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long i = 0; i < nmine; ++i) {
+    const int st = static_cast<int>(i % nstage);
+    const uint32_t ph = static_cast<uint32_t>((i / nstage) & 1);
+    const long long row = first + i * stride;
+    const float mean = __ldg(means + row);
+    const float rstd = rsqrtf(__ldg(vars + row) + kLnEps);
+    ln_mbar_wait(&full[st], ph);
+    const float4* sx = reinterpret_cast<const float4*>(ln_smem + static_cast<size_t>(st) * 2 * row_bytes);
+    const float4* sdy = reinterpret_cast<const float4*>(ln_smem + static_cast<size_t>(st) * 2 * row_bytes + row_bytes);
+    float4 xh[ITERS], dxh[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + t;
+      if (c < h4) {
+        xh[it] = sx[c];
+        dxh[it] = sdy[c];
+      } else {
+        xh[it] = make_float4(mean, mean, mean, mean);
+        dxh[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ln_smem_u32(&empty[st])) : "memory");  // stage is in registers
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const float4 dv = dxh[it];
+      xh[it] = make_float4((xh[it].x - mean) * rstd, (xh[it].y - mean) * rstd, (xh[it].z - mean) * rstd,
+                           (xh[it].w - mean) * rstd);
+      acc_b[it].x += dv.x, acc_b[it].y += dv.y, acc_b[it].z += dv.z, acc_b[it].w += dv.w;
+      acc_g[it].x += dv.x * xh[it].x, acc_g[it].y += dv.y * xh[it].y;
+      acc_g[it].z += dv.z * xh[it].z, acc_g[it].w += dv.w * xh[it].w;
+      dxh[it] = make_float4(dv.x * g4[it].x, dv.y * g4[it].y, dv.z * g4[it].z, dv.w * g4[it].w);
+      s1 += (dxh[it].x + dxh[it].y) + (dxh[it].z + dxh[it].w);
+      s2 += (dxh[it].x * xh[it].x + dxh[it].y * xh[it].y) + (dxh[it].z * xh[it].z + dxh[it].w * xh[it].w);
+    }
+    // row sums over the 256 compute threads (named barrier 1: the producer warp is not involved)
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (lane == 0) red2[warp] = make_float2(s1, s2);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s1 += red2[k].x, s2 += red2[k].y;
+    s1 *= inv_h;
+    s2 *= inv_h;
+    float4* dxr = reinterpret_cast<float4*>(dx + row * h);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + t;
+      if (c < h4) {
+        float4 o;
+        o.x = (dxh[it].x - s1 - xh[it].x * s2) * rstd;
+        o.y = (dxh[it].y - s1 - xh[it].y * s2) * rstd;
+        o.z = (dxh[it].z - s1 - xh[it].z * s2) * rstd;
+        o.w = (dxh[it].w - s1 - xh[it].w * s2) * rstd;
+        dxr[c] = o;
+      }
+    }
+  }
+  float4* pg = reinterpret_cast<float4*>(part_g + static_cast<size_t>(blockIdx.x) * h);
+  float4* pb = reinterpret_cast<float4*>(part_b + static_cast<size_t>(blockIdx.x) * h);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int c = it * 256 + t;
+    if (c < h4) pg[c] = acc_g[it], pb[c] = acc_b[it];
+  }
 }
 
 static int num_sms() {
@@ -309,6 +473,37 @@ int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, c
     return FA_OK;
   }
   int status = FA_OK;
+  if (hidden_dim >= 2048 && hidden_dim <= 4096) {
+    // wide rows: bulk-async staged kernel, two persistent CTAs per SM (two rows in flight per SM)
+    int grid = 2 * fa::num_sms();
+    if (grid > rows) grid = static_cast<int>(rows);
+    float* part = static_cast<float*>(fa::g_pool.get(8, sizeof(float) * 2 * static_cast<size_t>(grid) * hidden_dim));
+    if (!part) return fa::set_error(FA_ERR_CUDA, "layernorm_bw: workspace allocation failed");
+    float* part_g = part;
+    float* part_b = part + static_cast<size_t>(grid) * hidden_dim;
+    const size_t stage_bytes = static_cast<size_t>(hidden_dim) * 8;
+    int nstage = static_cast<int>((100 * 1024) / stage_bytes);
+    if (nstage > 8) nstage = 8;
+    const int smem = static_cast<int>(nstage * stage_bytes);
+    const int iters = (hidden_dim / 4 + 255) / 256;
+    auto launch = [&](auto kern) -> int {
+      FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<grid, 288, smem, s>>>(inp_grad, part_g, part_b, out_grad, inp, gamma, vars, means, rows, hidden_dim, nstage);
+      fa::count_launch();
+      FA_CUDA_CHECK(cudaGetLastError());
+      return FA_OK;
+    };
+    int rc = (iters == 1)   ? launch(fa::layernorm_bw_staged_kernel<1>)
+             : (iters == 2) ? launch(fa::layernorm_bw_staged_kernel<2>)
+             : (iters == 3) ? launch(fa::layernorm_bw_staged_kernel<3>)
+                            : launch(fa::layernorm_bw_staged_kernel<4>);
+    if (rc != FA_OK) return rc;
+    fa::ln_bw_reduce_kernel<<<(hidden_dim + 31) / 32, dim3(32, 32), 0, s>>>(gamma_grad, betta_grad, part_g, part_b, grid,
+                                                                            hidden_dim);
+    fa::count_launch();
+    FA_CUDA_CHECK(cudaGetLastError());
+    return FA_OK;
+  }
   bool ok = fa::dispatch_ln(hidden_dim / 4, [&]<int BLOCK, int TPR, int ITERS>() {
     constexpr int RPC = BLOCK / TPR;
     long long need = (rows + RPC - 1) / RPC;
@@ -326,7 +521,7 @@ int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, c
     fa::layernorm_bw_kernel<BLOCK, TPR, ITERS><<<grid, BLOCK, smem, s>>>(inp_grad, part_g, part_b, out_grad, inp,
                                                                          gamma, vars, means, rows, hidden_dim);
     fa::count_launch();
-    fa::ln_bw_reduce_kernel<<<(hidden_dim + 255) / 256, 256, 0, s>>>(gamma_grad, betta_grad, part_g, part_b, grid,
+    fa::ln_bw_reduce_kernel<<<(hidden_dim + 31) / 32, dim3(32, 32), 0, s>>>(gamma_grad, betta_grad, part_g, part_b, grid,
                                                                      hidden_dim);
     fa::count_launch();
   });

@@ -28,17 +28,25 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Block-wide reductions for the CTA-per-row variants (256 threads = 8 warps).
-template <bool IS_MAX>
-__device__ __forceinline__ float block_reduce(float v, float* red) {
+// Reduction over the TPR threads that own one row (TPR = 32: a warp shuffle; otherwise TPR/32
+// warps of the 256-thread CTA combine through shared memory; every thread of the CTA must call it).
+template <bool IS_MAX, int TPR>
+__device__ __forceinline__ float row_reduce(float v, float* red) {
   v = IS_MAX ? warp_max(v) : warp_sum(v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __syncthreads();  // protect `red` from the previous use
-  if (lane == 0) red[w] = v;
-  __syncthreads();
-  float r = (lane < nw) ? red[lane] : (IS_MAX ? -FLT_MAX : 0.f);
-  r = IS_MAX ? warp_max(r) : warp_sum(r);
-  return r;
+  if constexpr (TPR == 32) {
+    return v;
+  } else {
+    constexpr int WPG = TPR / 32;  // warps per row group
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();  // protect `red` from the previous use
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    const int g0 = (w / WPG) * WPG;
+    float r = red[g0];
+#pragma unroll
+    for (int i = 1; i < WPG; ++i) r = IS_MAX ? fmaxf(r, red[g0 + i]) : r + red[g0 + i];
+    return r;
+  }
 }
 
 template <int VEC>
@@ -83,8 +91,22 @@ __global__ void __launch_bounds__(256) attn_softmax_fw_kernel(float* __restrict_
   constexpr int ROWS_PER_CTA = 256 / TPR;
   const int sub = threadIdx.x / TPR;  // which row of this CTA
   const int t = threadIdx.x % TPR;    // thread within the row
-  for (long long row0 = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA; row0 < rows;
-       row0 += static_cast<long long>(gridDim.x) * ROWS_PER_CTA) {
+  // Software-pipelined row loop: the next row's values are requested before the two dependent
+  // reductions of the current row, so HBM latency overlaps the reduction latency.
+  const long long stride = static_cast<long long>(gridDim.x) * ROWS_PER_CTA;
+  float nv[ITERS][VEC];
+  auto fetch = [&](long long r0) {
+    const long long r = r0 + sub;
+    const float* xr = inp + ((r < rows) ? r : rows - 1) * to_len;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c0 = (it * TPR + t) * VEC;
+      if (c0 < to_len) load_vec<VEC>(xr + c0, nv[it]);
+    }
+  };
+  long long row0 = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA;
+  if (row0 < rows) fetch(row0);
+  for (; row0 < rows; row0 += stride) {
     const long long row = row0 + sub;
     const bool row_ok = row < rows;
     const long long rr = row_ok ? row : rows - 1;  // keep every thread in the collectives
@@ -99,7 +121,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fw_kernel(float* __restrict_
     for (int it = 0; it < ITERS; ++it) {
       const int c0 = (it * TPR + t) * VEC;
       if (c0 < to_len) {
-        load_vec<VEC>(x + c0, v[it]);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[it][k] = nv[it][k];
         if (mk) {
           float m4[VEC];
           load_vec<VEC>(mk + c0, m4);
@@ -118,7 +141,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fw_kernel(float* __restrict_
 #pragma unroll
       for (int k = 0; k < VEC; ++k) mx = fmaxf(mx, v[it][k]);
     }
-    mx = (TPR == 32) ? warp_max(mx) : block_reduce<true>(mx, red);
+    if (row0 + stride < rows) fetch(row0 + stride);
+    mx = row_reduce<true, TPR>(mx, red);
     float sum = 0.f;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -132,7 +156,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fw_kernel(float* __restrict_
         sum += e;
       }
     }
-    sum = (TPR == 32) ? warp_sum(sum) : block_reduce<false>(sum, red);
+    sum = row_reduce<false, TPR>(sum, red);
     const float inv = __fdividef(1.0f, sum + kSoftmaxEps);
     if (row_ok) {
 #pragma unroll
@@ -176,7 +200,7 @@ __global__ void __launch_bounds__(256) attn_softmax_bw_kernel(float* __restrict_
         for (int k = 0; k < VEC; ++k) s += gv[it][k] * yv[it][k];
       }
     }
-    s = (TPR == 32) ? warp_sum(s) : block_reduce<false>(s, red);
+    s = row_reduce<false, TPR>(s, red);
     if (row_ok) {
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
@@ -229,6 +253,26 @@ static bool dispatch_row(int len, bool aligned, F&& f) {
   return false;
 }
 
+// Forward dispatch: at most 4 values per thread up to 1024 columns (the two dependent reductions
+// make the row latency-bound, so occupancy matters more than work per thread: <32,4,16> at 2048
+// columns ran at 155 registers / 12% occupancy / 27% of HBM peak).
+template <typename F>
+static bool dispatch_row_fw(int len, bool aligned, F&& f) {
+  if (aligned && len % 4 == 0) {
+    const int v = len / 4;
+    if (v <= 32) return f.template operator()<32, 4, 1>(), true;
+    if (v <= 64) return f.template operator()<64, 4, 1>(), true;
+    if (v <= 128) return f.template operator()<128, 4, 1>(), true;
+    if (v <= 256) return f.template operator()<256, 4, 1>(), true;
+    if (v <= 512) return f.template operator()<256, 4, 2>(), true;
+    if (v <= 1024) return f.template operator()<256, 4, 4>(), true;
+    if (v <= 2048) return f.template operator()<256, 4, 8>(), true;
+    if (v <= 4096) return f.template operator()<256, 4, 16>(), true;
+    return false;
+  }
+  return dispatch_row(len, false, f);
+}
+
 static int grid_for(long long rows, int rows_per_cta) {
   long long need = (rows + rows_per_cta - 1) / rows_per_cta;
   long long cap = static_cast<long long>(num_sms()) * 16;  // 16 resident CTAs/SM worth of waves
@@ -251,7 +295,7 @@ int fa_attn_softmax_dev(float* inp, const float* attn_mask, int batch_size, int 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool aligned = (reinterpret_cast<uintptr_t>(inp) % 16 == 0) &&
                        (!attn_mask || reinterpret_cast<uintptr_t>(attn_mask) % 16 == 0);
-  bool ok = fa::dispatch_row(to_len, aligned, [&]<int TPR, int VEC, int ITERS>() {
+  bool ok = fa::dispatch_row_fw(to_len, aligned, [&]<int TPR, int VEC, int ITERS>() {
     fa::attn_softmax_fw_kernel<TPR, VEC, ITERS><<<fa::grid_for(rows, 256 / TPR), 256, 0, s>>>(
         inp, attn_mask, rows, nhead, from_len, to_len, mask_future);
     fa::count_launch();
