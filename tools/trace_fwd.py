@@ -44,4 +44,7 @@ for wg, name in enumerate(["g0 h0", "g1 h0", "g0 h1", "g1 h1"]):
     print(name)
     for j in range(4, 10):
         print(f"  {j:2d}  " + " ".join(f"{T[j, 8 + 4 * wg + k] - t0:8d}" for k in range(4)))
+print("MMA: before/after wait_full(V); g0h0 per-warp P-arrive times")
+for j in range(4, 10):
+    print(f"  {j:2d}  " + " ".join(f"{T[j, k] - t0:8d}" for k in (16, 17, 24, 25, 26, 27)))
 print("period per KV tile:", (T[12, 0] - T[4, 0]) / 8)
