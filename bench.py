@@ -43,6 +43,16 @@ WORKLOADS = {
 CPU_SAMPLE = dict(B=2, H=32, N=512, d=128)  # bounded sample of the same op for the CPU arms
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_kernel_shares.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_traffic_bytes_per_launch"][kernel])
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -78,7 +88,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Number of samples seen so far (call at the start of the timed region)."""
+        return len(self.rows)
+
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -88,7 +102,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:]:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -187,8 +201,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
@@ -238,17 +252,18 @@ def main():
         dev.flash_fwd(Q, K, V, causal=causal, kv_len=dkv, out=(O, m, l))
         dev.flash_bwd(Q, K, V, O, dO, m, l, causal=causal, kv_len=dkv, out=grads)
 
+    sampler = ClockSampler(local)
+    sampler.start()           # started before the warm-up: nvidia-smi needs ~1 s to emit its first line
     for _ in range(args.warmup):
         step()
     dev.sync()
 
     # ---- timed region: K steps, events around every fwd and bwd
     ev = [[lib.fa_event_create() for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
     launches0 = lib.fa_launch_count()
     barrier(dist)
     dev.sync()
-    sampler.start()
+    mark = sampler.mark()
     for i in range(args.steps):
         lib.fa_event_record(ev[i][0], None)
         dev.flash_fwd(Q, K, V, causal=causal, kv_len=dkv, out=(O, m, l))
@@ -257,8 +272,15 @@ def main():
         lib.fa_event_record(ev[i][2], None)
     dev.sync()
     barrier(dist)
-    clocks = sampler.stop()
     launches = int(lib.fa_launch_count() - launches0)
+    probe = 0
+    t_probe = time.perf_counter()
+    while sampler.mark() - mark < 4 and time.perf_counter() - t_probe < 3.0:
+        step()          # short timed regions: keep the same load running (untimed) until nvidia-smi has sampled it
+        dev.sync()
+        probe += 1
+    clocks = sampler.stop(mark)
+    clocks["untimed_probe_steps"] = probe
     total_ms = lib.fa_event_elapsed_ms(ev[0][0], ev[-1][2])
     fwd_ms = float(np.mean([lib.fa_event_elapsed_ms(e[0], e[1]) for e in ev]))
     bwd_ms = float(np.mean([lib.fa_event_elapsed_ms(e[1], e[2]) for e in ev]))
@@ -290,9 +312,11 @@ def main():
                        "flops": "effective (key padding excluded): fwd 4*H*d*sum_b N*kv_len[b], bwd 10*...",
                        "nominal_tflops": flops_nominal * world / (ms_per_step * 1e-3) / 1e12,
                        "l2": "inputs larger than L2 (8 tensors x 268 MB per GPU); no flush needed"},
-            "roofline": {"bound": "tensor", "kernel": f"flash {dom} (tcgen05)" if dom == "fwd" else "flash bwd",
+            "roofline": {"bound": "tensor", "kernel": f"sm100::{dom}_kernel (tcgen05/TMEM), timed with its pre/post passes",
                          "achieved": dom_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": dom_tf / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["source"]},
+                         "traffic": ncu_traffic(f"{dom}_kernel") if args.workload == "cfg4" else None,
+                         "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_kernel_shares.json)",
+                         "peak_source": peaks["source"]},
             "kernels": {"fwd_ms": fwd_ms, "fwd_tflops": fwd_tf, "fwd_frac_measured_sustained": fwd_tf / peaks["tflops"],
                         "fwd_frac_measured_burst": fwd_tf / peaks["burst"], "fwd_frac_datasheet_2250": fwd_tf / 2250.0,
                         "bwd_ms": bwd_ms, "bwd_tflops": bwd_tf, "bwd_frac_measured_sustained": bwd_tf / peaks["tflops"],
