@@ -38,6 +38,12 @@ WORKLOADS = {
                  desc="flash-attention fwd+bwd training step, B=8/GPU H=32 N=4096 d=128 bf16, key padding kv_len in [N/2,N]"),
     "cfg4_causal": dict(B=8, H=32, N=4096, d=128, causal=True, padding=True,
                         desc="cfg4 with a causal mask on top of key padding"),
+    # BASELINE config #5: batch 64 x 32 heads x seq 8192 x d 128, sharded by batch over the GPUs (strong scaling):
+    # B here is the GLOBAL batch; each rank takes B / world_size of it
+    "cfg5": dict(B=64, H=32, N=8192, d=128, causal=False, padding=False, strong=True,
+                 desc="batch x head-sharded attention fwd+bwd, global B=64 H=32 N=8192 d=128 bf16 (config #5)"),
+    "cfg5_causal": dict(B=64, H=32, N=8192, d=128, causal=True, padding=False, strong=True,
+                        desc="config #5 with a causal mask"),
     "small": dict(B=2, H=4, N=1024, d=128, causal=False, padding=True, desc="smoke-sized workload"),
 }
 CPU_SAMPLE = dict(B=2, H=32, N=512, d=128)  # bounded sample of the same op for the CPU arms
@@ -224,6 +230,8 @@ def main():
 
     w = WORKLOADS[args.workload]
     B, H, N, d, causal = w["B"], w["H"], w["N"], w["d"], w["causal"]
+    if w.get("strong"):
+        B = max(1, B // world)      # strong scaling: the global batch is split across the ranks
     rng = np.random.default_rng(1000 + rank)
     kv_len = rng.integers(N // 2, N + 1, B).astype(np.int32) if w["padding"] else None
 
@@ -306,7 +314,7 @@ def main():
         line = {
             "metric": "attention fwd+bwd TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["desc"], "per_gpu": {"B": B, "H": H, "N": N, "d": d, "causal": causal},
                        "parallelism": f"batch x head shards over {world} GPU(s), no collective",
                        "flops": "effective (key padding excluded): fwd 4*H*d*sum_b N*kv_len[b], bwd 10*...",
