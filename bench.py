@@ -139,27 +139,21 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
+def _agg(dist):
+    from flashattn_b200.sharding import Aggregator
+    return Aggregator(dist, "cuda")
+
+
 def barrier(dist):
-    if dist is not None:
-        dist.barrier()
+    _agg(dist).barrier()
 
 
 def reduce_max(dist, x):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    return _agg(dist).max(x)
 
 
 def reduce_sum(dist, x):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    return _agg(dist).sum(x)
 
 
 def cpu_reference_run(steps, warmup, cores=None):
@@ -230,8 +224,10 @@ def main():
 
     w = WORKLOADS[args.workload]
     B, H, N, d, causal = w["B"], w["H"], w["N"], w["d"], w["causal"]
-    if w.get("strong"):
-        B = max(1, B // world)      # strong scaling: the global batch is split across the ranks
+    if w.get("strong"):             # strong scaling: the global batch is split across the ranks
+        from flashattn_b200.sharding import shard_batch
+        b0, b1 = shard_batch(B, world, rank)
+        B = max(1, b1 - b0)
     rng = np.random.default_rng(1000 + rank)
     kv_len = rng.integers(N // 2, N + 1, B).astype(np.int32) if w["padding"] else None
 

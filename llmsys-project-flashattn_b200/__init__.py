@@ -7,11 +7,11 @@ Layout:
   tensor.py            stand-alone host tensor + FlashAttention / Attn_Softmax / LayerNorm autograd nodes
   device.py            device-resident buffers + the *_dev entry points (bench / sharded runs)
 """
-from . import _lib, device
+from . import _lib, device, sharding
 from ._lib import FlashAttnError
 from .cuda_kernel_ops import CudaKernelOps
 from .tensor import (Attn_Softmax, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
                      default_backend, tensor_from_numpy)
 
 __all__ = ["CudaKernelOps", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
-           "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device"]
+           "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding"]
