@@ -93,3 +93,39 @@ def test_legacy_abi_in_bf16_mode():
             assert maxabs(got.to_numpy(), want) < TOL
     finally:
         ops.set_flash_mode("fp32")
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_bf16_strided_bnhd_layout_through_tma(causal):
+    """(B,N,nh,d) storage -- MultiHeadAttention.project_to_query_key_value's layout before its permute
+    (modules_transfomer.py:87-100) -- consumed in place: the TMA descriptors carry the strides."""
+    rng = np.random.default_rng(21)
+    B, H, N, d = 2, 3, 320, 128
+    raw = [R.round_bf16(rng.standard_normal((B, N, H, d)).astype(np.float32)) for _ in range(4)]
+    Q, K, V, dO = (r.transpose(0, 2, 1, 3) for r in raw)
+    strides = (N * H * d, d, H * d)
+    dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(r, "bf16") for r in raw)
+    O, m, l = dev.flash_fwd(dq, dk, dv, causal=causal, shape=(B, H, N, d), strides=strides)
+    gq, gk, gv = dev.flash_bwd(dq, dk, dv, O, ddo, m, l, causal=causal, shape=(B, H, N, d), strides=strides)
+    Oe, _, _ = R.attention_fwd(Q, K, V, causal=causal)
+    ge = R.attention_bwd(Q, K, V, dO, causal=causal)
+    assert maxabs(O.to_numpy().transpose(0, 2, 1, 3), Oe) < TOL
+    for got, want, name in zip((gq, gk, gv), ge, ("dQ", "dK", "dV")):
+        ok, err = close_bf16(got.to_numpy().transpose(0, 2, 1, 3), want)
+        assert ok, (name, err)
+
+
+def test_bf16_reproducible_to_rounding():
+    """dQ is accumulated across KV-tile CTAs with fp32 add-reductions whose order varies; O, dK, dV are
+    bitwise reproducible, dQ to within fp32 summation noise (far below one bf16 ulp)."""
+    Q, K, V, dO = _inputs(1, 2, 640, 128, 33)
+    dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(x, "bf16") for x in (Q, K, V, dO))
+    runs = []
+    for _ in range(2):
+        O, m, l = dev.flash_fwd(dq, dk, dv, causal=True)
+        g = dev.flash_bwd(dq, dk, dv, O, ddo, m, l, causal=True)
+        runs.append([x.to_numpy() for x in (O,) + g])
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])
+    np.testing.assert_array_equal(runs[0][2], runs[1][2])
+    np.testing.assert_array_equal(runs[0][3], runs[1][3])
+    assert maxabs(runs[0][1], runs[1][1]) <= 2.0 ** -7 * max(1.0, float(np.abs(runs[0][1]).max()))

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Small-shape pass over every kernel family for compute-sanitizer (memcheck): fp32 + bf16 attention
+fwd/bwd (causal, ragged N, kv_len), softmax and layernorm fw/bw."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import flashattn_b200 as fb
+from flashattn_b200 import device as dev
+ops, T = fb.CudaKernelOps, fb.tensor_from_numpy
+rng = np.random.default_rng(0)
+for dtype, shapes in (("f32", [(1, 2, 39, 32, True), (1, 1, 130, 64, False)]),
+                      ("bf16", [(1, 2, 200, 128, True), (1, 1, 300, 64, False), (2, 1, 256, 128, False)])):
+    for (B, H, N, d, causal) in shapes:
+        Q, K, V, dO = (dev.DeviceArray.from_numpy(rng.standard_normal((B, H, N, d)).astype(np.float32), dtype) for _ in range(4))
+        kv = dev.DeviceArray.from_numpy(np.array([N - 7] * B, dtype=np.int32))
+        O, m, l = dev.flash_fwd(Q, K, V, causal=causal, kv_len=kv)
+        g = dev.flash_bwd(Q, K, V, O, dO, m, l, causal=causal, kv_len=kv)
+        dev.sync()
+        print("attention", dtype, (B, H, N, d, causal), "ok", float(np.abs(g[0].to_numpy()).max()))
+x = rng.uniform(-1, 1, (2, 2, 9, 100)).astype(np.float32)
+y = ops.attn_softmax_fw(T(x), T(np.zeros((2, 100), np.float32)))
+ops.attn_softmax_bw(T(x), y)
+for rows, h in ((33, 64), (5, 2048)):
+    a = rng.uniform(-1, 1, (rows, h)).astype(np.float32)
+    gm, bt = np.ones(h, np.float32), np.zeros(h, np.float32)
+    ln, var, mean = ops.layernorm_fw(T(a), T(gm), T(bt))
+    ops.layernorm_bw(T(a), T(a), T(gm), T(bt), var, mean)
+print("companions ok")
