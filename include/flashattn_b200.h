@@ -1,7 +1,7 @@
 /*
  * flashattn_b200.h -- C ABI of the B200-native fused-attention libraries.
  *
- * Three shared libraries are built by compile_cuda.sh under minitorch/cuda_kernels/,
+ * Four shared libraries are built by compile_cuda.sh under minitorch/cuda_kernels/,
  * with the SAME file names and the SAME legacy symbols the reference loads through
  * ctypes (reference: minitorch/cuda_kernel_ops.py:26-29), so the reference's own
  * cuda_kernel_ops.py binds them unchanged:
@@ -9,6 +9,7 @@
  *   flashattention_kernel.so   replaces src/flashattention_kernel.cu
  *   softmax_kernel.so          replaces src/softmax_kernel.cu
  *   layernorm_kernel.so        replaces src/layernorm_kernel.cu
+ *   combine.so                 replaces src/combine.cu (map / zip / reduce / matmul plumbing)
  *
  * Everything is plain pointers and ints: no torch / numpy types cross this boundary.
  * Tensors are row-major; "host" pointers are ordinary CPU memory (numpy storage),
@@ -148,6 +149,25 @@ int fa_layernorm_dev(float* ln_res, float* vars, float* means, const float* inp,
 int fa_layernorm_bw_dev(float* gamma_grad, float* betta_grad, float* inp_grad, const float* out_grad,
                         const float* inp, const float* gamma, const float* betta, const float* vars,
                         const float* means, long long rows, int hidden_dim, fa_stream_t stream);
+
+/* =====================================================================================
+ * combine.so   (reference: src/combine.cu:315, :385, :443, :523 -- SURVEY.md 8(f)-1 plumbing row)
+ * ===================================================================================== */
+/* Strided / broadcasting elementwise map, zip, single-dimension reduce and batched matmul over host
+ * fp32 storages described by int32 shape / stride arrays, with the reference's function ids
+ * (minitorch/cuda_kernel_ops.py:33-52: 1 add, 2 mul, 3 id, 4 neg, 5 lt, 6 eq, 7 sigmoid, 8 relu,
+ * 9 relu_back, 10 log, 11 log_back, 12 exp, 13 inv, 14 inv_back, 15 is_close, 16 max, 17 pow, 18 tanh).
+ * tensorReduce takes reduce_value as double: that is what the reference's ctypes binding passes
+ * (cuda_kernel_ops.py:217); its own C side declared float and therefore read garbage. */
+void tensorMap(float* out, int* out_shape, int* out_strides, int out_size, float* in_storage, int* in_shape,
+               int* in_strides, int in_size, int shape_size, int fn_id);
+void tensorZip(float* out, int* out_shape, int* out_strides, int out_size, int out_shape_size, float* a_storage,
+               int* a_shape, int* a_strides, int a_size, int a_shape_size, float* b_storage, int* b_shape,
+               int* b_strides, int b_size, int b_shape_size, int fn_id);
+void tensorReduce(float* out, int* out_shape, int* out_strides, int out_size, float* a_storage, int* a_shape,
+                  int* a_strides, int reduce_dim, double reduce_value, int shape_size, int fn_id);
+void MatrixMultiply(float* out, int* out_shape, int* out_strides, float* a_storage, int* a_shape, int* a_strides,
+                    float* b_storage, int* b_shape, int* b_strides, int batch, int m, int p);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,16 @@ SYMBOLS = {
     },
 }
 
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, ndim=1, flags="C_CONTIGUOUS")
+SYMBOLS["combine"] = {
+    **_COMMON,
+    "tensorMap": (None, [_f32, _i32, _i32, c_int, _f32, _i32, _i32, c_int, c_int, c_int]),
+    "tensorZip": (None, [_f32, _i32, _i32, c_int, c_int, _f32, _i32, _i32, c_int, c_int, _f32, _i32, _i32, c_int,
+                         c_int, c_int]),
+    "tensorReduce": (None, [_f32, _i32, _i32, c_int, _f32, _i32, _i32, c_int, c_double, c_int, c_int]),
+    "MatrixMultiply": (None, [_f32, _i32, _i32, _f32, _i32, _i32, _f32, _i32, _i32, c_int, c_int, c_int]),
+}
+
 _libs = {}
 
 

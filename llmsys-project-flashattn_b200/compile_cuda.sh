@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Build the three C-ABI shared libraries for sm_100a (B200), in-tree.
+# Build the four C-ABI shared libraries for sm_100a (B200), in-tree.
 # Mirrors the reference's compile_cuda.sh (same output names under minitorch/cuda_kernels/
 # so the reference's cuda_kernel_ops.py:26-29 can load them unchanged), but with an explicit
 # arch: tcgen05 / TMEM / TMA only exist for sm_100a.
@@ -11,7 +11,7 @@ mkdir -p "$OUT"
 NVCC="${NVCC:-nvcc}"
 FLAGS=(-std=c++20 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo --shared -Xcompiler -fPIC "$@")
 pids=()
-for name in flashattention_kernel softmax_kernel layernorm_kernel; do
+for name in flashattention_kernel softmax_kernel layernorm_kernel combine; do
   "$NVCC" "${FLAGS[@]}" -o "$OUT/$name.so" "$HERE/csrc/$name.cu" &
   pids+=($!)
 done

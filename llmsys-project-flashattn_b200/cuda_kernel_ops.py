@@ -46,8 +46,145 @@ def _mask_ptr(key_mask, B, N):
     return km, km.ctypes.data_as(_lib.c_void_p)
 
 
+# function ids of the combine.so switch (minitorch/cuda_kernel_ops.py:33-52, src/combine.cu:11-28).  Keys are
+# the operator NAMES so that the reference's ``minitorch.operators`` callables (looked up through
+# ``__name__``), plain strings and raw ids all resolve.
+fn_map = {"add": 1, "mul": 2, "id": 3, "neg": 4, "lt": 5, "eq": 6, "sigmoid": 7, "relu": 8, "relu_back": 9,
+          "log": 10, "log_back": 11, "exp": 12, "inv": 13, "inv_back": 14, "is_close": 15, "max": 16, "pow": 17,
+          "tanh": 18}
+
+
+def _fn_id(fn) -> int:
+    if isinstance(fn, int):
+        return fn
+    name = fn if isinstance(fn, str) else getattr(fn, "__name__", None)
+    if name not in fn_map:
+        raise KeyError(f"{fn!r} is not one of the 18 functions combine.so implements")  # reference: KeyError too
+    return fn_map[name]
+
+
+def _i32(seq) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(seq, dtype=np.int32).reshape(-1))
+
+
+def _layout(t):
+    d = t._tensor
+    shape = getattr(d, "_shape", None)
+    strides = getattr(d, "_strides", None)
+    return _i32(d.shape if shape is None else shape), _i32(d.strides if strides is None else strides)
+
+
+def shape_broadcast(s1, s2):
+    """minitorch/tensor_data.py shape_broadcast: right-aligned numpy-style union."""
+    n = max(len(s1), len(s2))
+    a, b = (1,) * (n - len(s1)) + tuple(s1), (1,) * (n - len(s2)) + tuple(s2)
+    out = []
+    for x, y in zip(a, b):
+        if x != y and x != 1 and y != 1:
+            raise IndexError(f"cannot broadcast {tuple(s1)} with {tuple(s2)}")
+        out.append(max(x, y))
+    return tuple(out)
+
+
+def _size(t) -> int:
+    return int(np.prod(t.shape)) if len(t.shape) else 1
+
+
 class CudaKernelOps:
     cuda = True
+
+    # ------------------------------------------------------------------ map / zip / reduce / matmul
+    # (minitorch/cuda_kernel_ops.py:58-437 over combine.so; SURVEY.md 8(f)-1)
+    @staticmethod
+    def map(fn):
+        fn_id = _fn_id(fn)
+
+        def ret(a, out=None):
+            lib = _lib.load("combine")
+            if out is None:
+                out = a.zeros(a.shape)
+            osh, ost = _layout(out)
+            ash, ast = _layout(a)
+            if len(ash) < len(osh):      # `out` given with more dims: right-align like broadcast_index
+                pad = len(osh) - len(ash)
+                ash = _i32([1] * pad + list(ash))
+                ast = _i32([0] * pad + list(ast))
+            lib.tensorMap(_storage(out), osh, ost, _size(out), _storage(a), ash, ast, _size(a), len(osh), fn_id)
+            _lib.check(lib)
+            return out
+
+        return ret
+
+    @staticmethod
+    def zip(fn):
+        fn_id = _fn_id(fn)
+
+        def ret(a, b):
+            lib = _lib.load("combine")
+            out = a.zeros(shape_broadcast(a.shape, b.shape))
+            osh, ost = _layout(out)
+            ash, ast = _layout(a)
+            bsh, bst = _layout(b)
+            lib.tensorZip(_storage(out), osh, ost, _size(out), len(osh), _storage(a), ash, ast, _size(a), len(ash),
+                          _storage(b), bsh, bst, _size(b), len(bsh), fn_id)
+            _lib.check(lib)
+            return out
+
+        return ret
+
+    @staticmethod
+    def reduce(fn, start: float = 0.0):
+        fn_id = _fn_id(fn)
+
+        def ret(a, dim: int):
+            lib = _lib.load("combine")
+            out_shape = list(a.shape)
+            out_shape[dim] = 1
+            out = a.zeros(tuple(out_shape))
+            osh, ost = _layout(out)
+            ash, ast = _layout(a)
+            lib.tensorReduce(_storage(out), osh, ost, _size(out), _storage(a), ash, ast, int(dim), float(start),
+                             len(ash), fn_id)
+            _lib.check(lib)
+            return out
+
+        return ret
+
+    @staticmethod
+    def matrix_multiply(a, b):
+        """Batched matmul with the reference's shape handling (:343-437): 2-D operands become a batch of
+        one (broadcast against the other side), >3-D operands are flattened over their leading dims."""
+        lib = _lib.load("combine")
+        both_2d = 0
+        if len(a.shape) == 2:
+            a = a.contiguous().view(1, a.shape[0], a.shape[1])
+            both_2d += 1
+        if len(b.shape) == 2:
+            b = b.contiguous().view(1, b.shape[0], b.shape[1])
+            both_2d += 1
+        both_2d = both_2d == 2
+        ls = list(shape_broadcast(a.shape[:-2], b.shape[:-2])) + [a.shape[-2], b.shape[-1]]
+        if a.shape[-1] != b.shape[-2]:
+            raise AssertionError(f"matmul inner dims differ: {a.shape} @ {b.shape}")
+        out = a.zeros(tuple(ls))
+        more_3d = len(ls) > 3
+        if more_3d:
+            out = out.view(int(np.prod(ls[:-2])), ls[-2], ls[-1])
+        if len(a.shape) > 3:
+            a = a.contiguous().view(int(np.prod(a.shape[:-2])), a.shape[-2], a.shape[-1])
+        if len(b.shape) > 3:
+            b = b.contiguous().view(int(np.prod(b.shape[:-2])), b.shape[-2], b.shape[-1])
+        osh, ost = _layout(out)
+        ash, ast = _layout(a)
+        bsh, bst = _layout(b)
+        lib.MatrixMultiply(_storage(out), osh, ost, _storage(a), ash, ast, _storage(b), bsh, bst, out.shape[0],
+                           a.shape[1], b.shape[2])
+        _lib.check(lib)
+        if both_2d:
+            out = out.view(out.shape[1], out.shape[2])
+        if more_3d:
+            out = out.view(*ls)
+        return out
 
     # ------------------------------------------------------------------ flash attention
     @staticmethod

@@ -28,6 +28,18 @@ class TensorBackend:
     def __init__(self, ops=CudaKernelOps):
         self.ops = ops
         self.cuda = getattr(ops, "cuda", False)
+        if hasattr(ops, "map"):   # map / zip / reduce / matmul over combine.so, same attribute names as the reference
+            for name in ("neg", "sigmoid", "relu", "log", "exp", "id", "inv", "tanh"):
+                setattr(self, name + "_map", ops.map(name))
+            self.id_cmap = self.id_map
+            for name in ("add", "mul", "lt", "eq", "is_close", "relu_back", "log_back", "inv_back"):
+                setattr(self, name + "_zip", ops.zip(name))
+            self.pow_scalar_zip = ops.zip("pow")
+            self.max_zip = ops.zip("max")
+            self.add_reduce = ops.reduce("add", 0.0)
+            self.mul_reduce = ops.reduce("mul", 1.0)
+            self.max_reduce = ops.reduce("max", -1e9)
+            self.matrix_multiply = ops.matrix_multiply
         for name in ("attn_softmax_fw", "attn_softmax_bw", "layernorm_fw", "layernorm_bw", "flash_attention_fw",
                      "flash_attention_bw", "flash_attention_causal_fw", "flash_attention_causal_bw"):
             setattr(self, name, getattr(ops, name))
@@ -46,6 +58,14 @@ class _Data:
                 acc *= s
             strides = tuple(reversed(st))
         self.strides = tuple(int(s) for s in strides)
+
+    @property
+    def _shape(self) -> np.ndarray:      # minitorch.TensorData attribute names
+        return np.array(self.shape, dtype=np.int32)
+
+    @property
+    def _strides(self) -> np.ndarray:
+        return np.array(self.strides, dtype=np.int32)
 
     def is_contiguous(self) -> bool:
         exp = 1
@@ -109,6 +129,10 @@ class HostTensor:
     @property
     def shape(self):
         return self._tensor.shape
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape)) if self.shape else 1
 
     def contiguous(self) -> "HostTensor":
         if self._tensor.is_contiguous():

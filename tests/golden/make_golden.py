@@ -206,8 +206,62 @@ def gen_layernorm():
         print("layernorm", name, x.shape)
 
 
+def gen_combine():
+    """The reference's own CPU implementation of the combine.so surface: FastOps.map / zip / reduce /
+    matrix_multiply (minitorch/fast_ops.py:154-353) over its scalar operators (minitorch/operators.py),
+    the same function table src/combine.cu:31-117 switches on (ids: cuda_kernel_ops.py:33-52)."""
+    from minitorch import operators as ops
+    rng = np.random.default_rng(5)
+    out = {}
+    a = rng.uniform(-2, 2, (3, 4, 5)).astype(datatype)
+    a[0, 0, :3] = [0.0, 0.5, -0.5]
+    b = rng.uniform(-2, 2, (3, 4, 5)).astype(datatype)
+    b[1, 2, :] = a[1, 2, :]                      # exact ties for eq / is_close / lt
+    b[2, 0, :] = a[2, 0, :] + 0.005
+    pos = np.abs(a) + 0.1                        # domain of log / pow
+    brow = rng.uniform(-2, 2, (1, 5)).astype(datatype)   # right-aligned broadcast operand
+    nz = np.where(np.abs(a) < 0.1, datatype(0.3), a)     # inv(0) raises under numba (Python semantics)
+    out.update(a=a, b=b, pos=pos, brow=brow, nz=nz)
+    for name in ("id", "neg", "sigmoid", "relu", "exp", "tanh"):
+        out[f"map_{name}"] = FastOps.map(getattr(ops, name))(mt(a, False)).to_numpy()
+    out["map_inv"] = FastOps.map(ops.inv)(mt(nz, False)).to_numpy()
+    out["map_log"] = FastOps.map(ops.log)(mt(pos, False)).to_numpy()
+    # strided input view: map over a permuted tensor
+    out["map_neg_perm"] = FastOps.map(ops.neg)(mt(a, False).permute(2, 0, 1)).to_numpy()
+    out["zip_inv_back"] = FastOps.zip(ops.inv_back)(mt(nz, False), mt(b, False)).to_numpy()
+    out["zipb_inv_back"] = FastOps.zip(ops.inv_back)(mt(nz, False), mt(brow, False)).to_numpy()
+    for name in ("add", "mul", "lt", "eq", "relu_back", "is_close", "max"):
+        out[f"zip_{name}"] = FastOps.zip(getattr(ops, name))(mt(a, False), mt(b, False)).to_numpy()
+        out[f"zipb_{name}"] = FastOps.zip(getattr(ops, name))(mt(a, False), mt(brow, False)).to_numpy()
+    out["zip_log_back"] = FastOps.zip(ops.log_back)(mt(pos, False), mt(b, False)).to_numpy()
+    out["zip_pow"] = FastOps.zip(ops.pow)(mt(pos, False), mt(b, False)).to_numpy()
+    out["zip_add_perm"] = FastOps.zip(ops.add)(mt(a, False).permute(1, 0, 2), mt(b, False).permute(1, 0, 2)).to_numpy()
+    for dim in (0, 1, 2):
+        out[f"red_add_{dim}"] = FastOps.reduce(ops.add, 0.0)(mt(a, False), dim).to_numpy()
+        out[f"red_mul_{dim}"] = FastOps.reduce(ops.mul, 1.0)(mt(a, False), dim).to_numpy()
+        out[f"red_max_{dim}"] = FastOps.reduce(ops.max, -1e9)(mt(a, False), dim).to_numpy()
+    big = rng.uniform(-1, 1, (2, 700, 3)).astype(datatype)
+    out["big"] = big
+    out["red_add_big"] = FastOps.reduce(ops.add, 0.0)(mt(big, False), 1).to_numpy()
+    # matmul: batched, batch-broadcast (2-D weight), transposed (permuted) operand, ragged tile sizes
+    A = rng.standard_normal((4, 37, 70)).astype(datatype)
+    Bm = rng.standard_normal((4, 70, 29)).astype(datatype)
+    W = rng.standard_normal((70, 29)).astype(datatype)
+    Kt = rng.standard_normal((4, 29, 70)).astype(datatype)
+    out.update(mm_A=A, mm_B=Bm, mm_W=W, mm_Kt=Kt)
+    out["mm_batched"] = FastOps.matrix_multiply(mt(A, False), mt(Bm, False)).to_numpy()
+    out["mm_bcast"] = FastOps.matrix_multiply(mt(A, False), mt(W, False)).to_numpy()
+    out["mm_transposed"] = FastOps.matrix_multiply(mt(A, False), mt(Kt, False).permute(0, 2, 1)).to_numpy()
+    np.savez_compressed(os.path.join(HERE, "combine_ops.npz"), **out)
+    print("combine", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "combine":
+        gen_combine()
+        sys.exit(0)
     gen_attention()
     gen_mha()
     gen_softmax()
     gen_layernorm()
+    gen_combine()

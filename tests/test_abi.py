@@ -17,7 +17,7 @@ HEADER = os.path.join(ROOT, "include", "flashattn_b200.h")
 def _declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b((?:fa_|launch_)[A-Za-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b((?:fa_|launch_)[A-Za-z0-9_]+|tensorMap|tensorZip|tensorReduce|MatrixMultiply)\s*\(", src)
     return sorted(set(n for n in names if n not in ("fa_stream_t",)))
 
 
@@ -48,6 +48,8 @@ def test_every_header_symbol_is_exported():
         assert hasattr(libs["softmax_kernel"], sym)
     for sym in ("launch_layernorm", "launch_layernorm_bw"):
         assert hasattr(libs["layernorm_kernel"], sym)
+    for sym in ("tensorMap", "tensorZip", "tensorReduce", "MatrixMultiply"):   # cuda_kernel_ops.py:26 combine.so
+        assert hasattr(libs["combine"], sym)
 
 
 @needs_build

@@ -96,3 +96,29 @@ def test_numba_port_matches_reference_composed(name):
     np.testing.assert_allclose(dQ, z["dQ"], atol=3e-5, rtol=1e-4)
     np.testing.assert_allclose(dK, z["dK"], atol=3e-5, rtol=1e-4)
     np.testing.assert_allclose(dV, z["dV"], atol=3e-5, rtol=1e-4)
+
+
+def test_combine_oracle_matches_reference_fastops():
+    """oracle/combine_ref.py against tests/golden/combine_ops.npz (the reference's own FastOps
+    map/zip/reduce/matrix_multiply outputs, generated by tests/golden/make_golden.py)."""
+    from oracle import combine_ref as C
+    g = np.load(os.path.join(G, "combine_ops.npz"))
+    tol = dict(rtol=2e-6, atol=2e-6)
+    for name in C.UNARY:
+        src = {"log": "pos", "inv": "nz"}.get(name, "a")
+        np.testing.assert_allclose(C.tensor_map(C.FN_IDS[name], g[src]), g[f"map_{name}"], **tol)
+    np.testing.assert_allclose(C.tensor_map(4, np.transpose(g["a"], (2, 0, 1))), g["map_neg_perm"], **tol)
+    for name in C.BINARY:
+        a = {"log_back": "pos", "pow": "pos", "inv_back": "nz"}.get(name, "a")
+        np.testing.assert_allclose(C.tensor_zip(C.FN_IDS[name], g[a], g["b"]), g[f"zip_{name}"], **tol)
+        if f"zipb_{name}" in g.files:
+            np.testing.assert_allclose(C.tensor_zip(C.FN_IDS[name], g[a], g["brow"]), g[f"zipb_{name}"], **tol)
+    for dim in (0, 1, 2):
+        np.testing.assert_allclose(C.tensor_reduce(1, g["a"], dim, 0.0), g[f"red_add_{dim}"], rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(C.tensor_reduce(2, g["a"], dim, 1.0), g[f"red_mul_{dim}"], rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(C.tensor_reduce(16, g["a"], dim, -1e9), g[f"red_max_{dim}"], **tol)
+    np.testing.assert_allclose(C.tensor_reduce(1, g["big"], 1, 0.0), g["red_add_big"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(C.matrix_multiply(g["mm_A"], g["mm_B"]), g["mm_batched"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(C.matrix_multiply(g["mm_A"], g["mm_W"]), g["mm_bcast"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(C.matrix_multiply(g["mm_A"], np.swapaxes(g["mm_Kt"], 1, 2)), g["mm_transposed"],
+                               rtol=1e-5, atol=2e-5)

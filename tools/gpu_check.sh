@@ -13,6 +13,7 @@ for g in $groups; do
     diag_fwd) run diag_fwd python tools/diag_fwd.py ;;
     diag_bwd) run diag_bwd python tools/diag_bwd.py ;;
     flash_bf16) run flash_bf16 python -m pytest tests/test_gpu_flash_bf16.py -q -m gpu ;;
+    combine) run combine python -m pytest tests/test_gpu_combine.py -q -m gpu ;;
     mha) run mha python -m pytest tests/test_gpu_mha_integration.py -q -m gpu ;;
     extra) run extra python tools/bench_extra.py --out gpurun_out/extra.json ;;
     alltests) run alltests python -m pytest tests -x -q -m gpu ;;
