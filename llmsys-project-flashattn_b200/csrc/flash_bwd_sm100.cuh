@@ -306,68 +306,88 @@ __global__ void __launch_bounds__(384, 1)
       __syncwarp();
     } else if (warp == 9) {
       // ---------------------------------------------------------------- MMA issuer
-      if (lane == 0) {
+      // The whole warp walks the schedule (uniform control flow keeps the descriptors in uniform
+      // registers: no per-lane serialisation loop around every tcgen05.mma); one elected lane issues.
+      {
+        const bool leader = elect_one();
         constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_kn = make_idesc_bf16(128, D, 0, 1);   // A K-major / TMEM, B MN-major
         constexpr uint32_t idesc_mn = make_idesc_bf16(128, D, 1, 1);   // A MN-major, B MN-major
         const uint32_t tS = tmem_base + Cfg::T_S, tdP = tmem_base + Cfg::T_DP;
         const uint32_t tdV = tmem_base + Cfg::T_DV, tdK = tmem_base + Cfg::T_DK;
-        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sdS), adO = smem_u32(sdO);
+        // descriptor low words (address >> 4 | LBO) per tile and the two high words (K-major / MN-major)
+        const uint64_t dkm = make_smem_desc(smem_u32(sK), 16, 1024);
+        const uint64_t dmn = make_smem_desc(smem_u32(sK), Cfg::CHUNK_BYTES, 1024);
+        const uint32_t km_hi = static_cast<uint32_t>(dkm >> 32), mn_hi = static_cast<uint32_t>(dmn >> 32);
+        const uint32_t km_lo0 = static_cast<uint32_t>(dkm), mn_lo0 = static_cast<uint32_t>(dmn);
+        auto km_lo = [&](const uint8_t* ptr) { return km_lo0 + ((smem_u32(ptr) - smem_u32(sK)) >> 4); };
+        auto mn_lo = [&](const uint8_t* ptr) { return mn_lo0 + ((smem_u32(ptr) - smem_u32(sK)) >> 4); };
+        const uint32_t kK = km_lo(sK), kV = km_lo(sV), kdO = km_lo(sdO), kDS = km_lo(sdS);
+        const uint32_t mK = mn_lo(sK), mdO = mn_lo(sdO), mDS = mn_lo(sdS);
+        auto commit = [&](uint64_t* bar) {
+          if (leader) mma_commit(bar);
+        };
         // [128 x 128] = X[128 x D] * Y[128 x D]^T : both operands K-major over the head dim
         auto issue_nt = [&](uint32_t dst, uint32_t xa, uint32_t ya) {
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32;
-            mma_ss(dst, make_smem_desc(xa + off, 16, 1024), make_smem_desc(ya + off, 16, 1024), idesc_s, k > 0);
+            for (int k = 0; k < D / 16; ++k) {
+              const uint32_t off = ((k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32) >> 4;
+              mma_ss2(dst, xa + off, km_hi, ya + off, km_hi, idesc_s, k > 0);
+            }
           }
         };
         mbar_wait(kv_full, 0);
         mbar_wait(&q_full[0], 0);
         tc_fence_after();
-        issue_nt(tS, aK, smem_u32(sQ));
-        mma_commit(&s_full[0]);
+        issue_nt(tS, kK, km_lo(sQ));
+        commit(&s_full[0]);
         mbar_wait(do_full, 0);
         tc_fence_after();
-        issue_nt(tdP, aV, adO);
-        mma_commit(&dp_full[0]);
+        issue_nt(tdP, kV, kdO);
+        commit(&dp_full[0]);
         for (int it = 0; it < n_iter; ++it) {
           const int s = it & 1, ph = (it >> 1) & 1;
-          const uint32_t aQ = smem_u32(sQ + s * Cfg::TILE_BYTES);
+          const uint32_t mQ = mn_lo(sQ + s * Cfg::TILE_BYTES);
           // dV += P^T dO_i : A = P^T in TMEM (bf16, 8 columns per 16 queries), B = dO_i as [K=q][N=d]
           mbar_wait(&p_full[s], ph);
           tc_fence_after();
           FA_TR(0)
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            mma_ts(tdV, tS + k * 8, make_smem_desc(adO + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn,
-                   (it > 0 || k > 0) ? 1u : 0u);
-          mma_commit(do_empty);   // dO_i is dead once dV(i) has run (dP(i) ran earlier)
+            for (int k = 0; k < 8; ++k)
+              mma_ts2(tdV, tS + k * 8, mdO + k * (2048 >> 4), mn_hi, idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          commit(do_empty);   // dO_i is dead once dV(i) has run (dP(i) ran earlier)
           FA_TR(1)
           if (it + 1 < n_iter) {
             const int s1 = (it + 1) & 1;
             mbar_wait(&q_full[s1], ((it + 1) >> 1) & 1);
             tc_fence_after();
             FA_TR(2)
-            issue_nt(tS, aK, smem_u32(sQ + s1 * Cfg::TILE_BYTES));
-            mma_commit(&s_full[s1]);
+            issue_nt(tS, kK, km_lo(sQ + s1 * Cfg::TILE_BYTES));
+            commit(&s_full[s1]);
             FA_TR(3)
           }
           mbar_wait(&ds_full[s], ph);
           tc_fence_after();
           FA_TR(4)
-          // dQ_i = dS K : A = dS^T tile read MN-major ([K=key][M=q]), B = K tile as [K=key][N=d]
+          if (leader) {
+            // dQ_i = dS K : A = dS^T tile read MN-major ([K=key][M=q]), B = K tile as [K=key][N=d]
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            mma_ss(tdP, make_smem_desc(aDS + k * 2048, Cfg::CHUNK_BYTES, 1024),
-                   make_smem_desc(aK + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_mn, k > 0);
-          mma_commit(&dq_full[s]);
-          // dK += dS^T Q_i : A = dS^T tile K-major ([M=key][K=q]), B = Q_i as [K=q][N=d]
+            for (int k = 0; k < 8; ++k)
+              mma_ss2(tdP, mDS + k * (2048 >> 4), mn_hi, mK + k * (2048 >> 4), mn_hi, idesc_mn, k > 0);
+          }
+          commit(&dq_full[s]);
+          if (leader) {
+            // dK += dS^T Q_i : A = dS^T tile K-major ([M=key][K=q]), B = Q_i as [K=q][N=d]
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            mma_ss(tdK, make_smem_desc(aDS + (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32, 16, 1024),
-                   make_smem_desc(aQ + k * 2048, Cfg::CHUNK_BYTES, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
-          mma_commit(&ds_empty[s]);
-          mma_commit(&q_empty[s]);
+            for (int k = 0; k < 8; ++k)
+              mma_ss2(tdK, kDS + (((k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32) >> 4), km_hi, mQ + k * (2048 >> 4),
+                      mn_hi, idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          commit(&ds_empty[s]);
+          commit(&q_empty[s]);
           FA_TR(5)
           if (it + 1 < n_iter) {
             const int s1 = (it + 1) & 1;
@@ -375,12 +395,12 @@ __global__ void __launch_bounds__(384, 1)
             mbar_wait(&dq_free[s], ph);
             tc_fence_after();
             FA_TR(6)
-            issue_nt(tdP, aV, adO);
-            mma_commit(&dp_full[s1]);
+            issue_nt(tdP, kV, kdO);
+            commit(&dp_full[s1]);
             FA_TR(7)
           }
         }
-        mma_commit(dkv_done);
+        commit(dkv_done);
       }
       __syncwarp();
     } else if (warp == 10) {

@@ -9,7 +9,9 @@
 //                the two halves agree on the row max through a 4 KB shared-memory exchange.
 //   warp 16    : TMA producer (Q tiles once; K,V tiles through an NSTAGE ring)
 //   warp 17    : tcgen05.mma issuer (one lane) + TMEM allocation
-//   (18 warps = 576 threads -> 112 registers per thread without any setmaxnreg juggling)
+//   warps 18-19: idle (they only complete the helper warpgroup so that setmaxnreg can move registers:
+//                20 warps launch with 96 registers each; the softmax warpgroups grow to 104, the helper
+//                warpgroup shrinks to 64)
 // TMEM (512 columns): S0 | S1 (128 fp32 columns each), O0 | O1 (D columns each).  P (bf16)
 // overwrites the first 64 columns of its S tile and is consumed directly from TMEM as the
 // A operand of the PV MMA, so P never touches shared memory.
@@ -54,7 +56,7 @@ struct FwdCfg {
   static constexpr int XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [parity][tile][half][row] fp32 row-max / row-sum exchange
   static constexpr int SMEM_BYTES = SMEM_TILES + XCHG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
-  static constexpr int NTHREADS = 576;
+  static constexpr int NTHREADS = 640;
 };
 
 __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* r) {
@@ -85,13 +87,19 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
   }
 }
 
+// scheduling fence: everything that produces these registers is ordered before the next volatile asm
+__device__ __forceinline__ void pin16(const uint32_t (&r)[16], float f) {
+  asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+               "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "f"(f));
+}
+
 #ifndef FA_FWD_EMU
 #define FA_FWD_EMU 0   // exponentials per 8 evaluated on the FMA pipe instead of MUFU (measured on B200:
                        // 0 -> 1.53 ms, 2 -> 1.62 ms, 3 -> 1.75 ms at cfg4: the FP32 pipe is the busier one, so off)
 #endif
 // MASKMODE: 0 none (N-ragged only), 1 kv_len[b], 2 additive key mask (B,N)
 template <int D, bool CAUSAL, int MASKMODE, typename OutT>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __launch_bounds__(640, 1)
     fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<D>;
@@ -108,8 +116,9 @@ __global__ void __launch_bounds__(576, 1)
   uint64_t* kv_full = bars + 2;            // [NSTAGE]
   uint64_t* kv_empty = kv_full + NSTAGE;   // [NSTAGE]
   uint64_t* s_full = kv_empty + NSTAGE;    // [2]
-  uint64_t* p_full = s_full + 2;           // [2]
-  uint64_t* o_done = p_full + 2;           // [2]
+  uint64_t* p_lo = s_full + 2;             // [2]  P of keys [0,64) of the tile written
+  uint64_t* p_hi = p_lo + 2;               // [2]  P of keys [64,128) written
+  uint64_t* o_done = p_hi + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,7 +145,8 @@ __global__ void __launch_bounds__(576, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 256);
+      mbar_init(&p_lo[i], 256);
+      mbar_init(&p_hi[i], 256);
       mbar_init(&o_done[i], 1);
     }
     for (int i = 0; i < NSTAGE; ++i) {
@@ -152,6 +162,7 @@ __global__ void __launch_bounds__(576, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 16) {
+   reg_dealloc<64>();
    if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -178,33 +189,48 @@ __global__ void __launch_bounds__(576, 1)
     __syncwarp();
   } else if (warp == 17) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && nk > 0) {
+    // The whole warp walks the schedule (uniform control flow, so the descriptors live in uniform
+    // registers and no per-lane serialisation loop is generated); one elected lane issues.
+    if (nk > 0) {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
       const uint32_t tS[2] = {tmem_base + Cfg::S_COL0, tmem_base + Cfg::S_COL1};
       const uint32_t tO[2] = {tmem_base + Cfg::O_COL0, tmem_base + Cfg::O_COL1};
-      auto stage_addr = [&](int t) { return smem_u32(sKV + (t % NSTAGE) * Cfg::TILE_BYTES); };
+      // descriptor = {low word: (address >> 4) | LBO field, high word: SBO | version | swizzle}
+      const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t dk = make_smem_desc(smem_u32(sKV), 16, 1024);
+      const uint64_t dv = make_smem_desc(smem_u32(sKV), Cfg::CHUNK_BYTES, 1024);
+      const uint32_t q_lo = static_cast<uint32_t>(dq), k_lo = static_cast<uint32_t>(dk),
+                     v_lo = static_cast<uint32_t>(dv);
+      const uint32_t kq_hi = static_cast<uint32_t>(dk >> 32), v_hi = static_cast<uint32_t>(dv >> 32);
       auto wait_full = [&](int t) {
         mbar_wait(&kv_full[t % NSTAGE], (t / NSTAGE) & 1);
         tc_fence_after();
       };
       // S_g = Q_g K^T : A = Q (K-major), B = K tile (K-major), 16 head-dim elements per MMA
       auto issue_qk = [&](int g, int t) {
-        const uint32_t qa = smem_u32(sQ + g * Cfg::TILE_BYTES), ka = stage_addr(t);
+        const uint32_t qa = q_lo + g * (Cfg::TILE_BYTES >> 4), ka = k_lo + (t % NSTAGE) * (Cfg::TILE_BYTES >> 4);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32;
-          mma_ss(tS[g], make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk, k > 0);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = ((k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32) >> 4;
+            mma_ss2(tS[g], qa + off, kq_hi, ka + off, kq_hi, idesc_qk, k > 0);
+          }
         }
       };
       // O_g += P_g V : A = P (bf16 in TMEM, 8 columns per 16 keys), B = V tile (MN-major), 16 keys per MMA
-      auto issue_pv = [&](int g, int t, bool acc) {
-        const uint32_t va = stage_addr(t);
+      // (issued in two halves of 64 keys so the first half overlaps the second half of the softmax)
+      auto issue_pv = [&](int g, int t, bool acc, int half) {
+        const uint32_t va = v_lo + (t % NSTAGE) * (Cfg::TILE_BYTES >> 4);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t bdesc = make_smem_desc(va + k * 2048, Cfg::CHUNK_BYTES, 1024);
-          mma_ts(tO[g], tS[g] + k * 8, bdesc, idesc_pv, (acc || k > 0) ? 1u : 0u);
+          for (int k = 4 * half; k < 4 * half + 4; ++k)
+            mma_ts2(tO[g], tS[g] + k * 8, va + k * (2048 >> 4), v_hi, idesc_pv, (acc || k > 0) ? 1u : 0u);
         }
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader) mma_commit(bar);
       };
       wait_full(0);
 #pragma unroll
@@ -213,10 +239,10 @@ __global__ void __launch_bounds__(576, 1)
           mbar_wait(&q_full[g], 0);
           tc_fence_after();
           issue_qk(g, 0);
-          mma_commit(&s_full[g]);
+          commit(&s_full[g]);
         }
       }
-      mma_commit(&kv_empty[0]);
+      commit(&kv_empty[0]);
       for (int j = 0; j < nk; ++j) {
         const int tv = 2 * j + 1, tk = 2 * j + 2;
         wait_full(tv);
@@ -224,11 +250,14 @@ __global__ void __launch_bounds__(576, 1)
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (j < nkv[g]) {
-            mbar_wait(&p_full[g], j & 1);
+            mbar_wait(&p_lo[g], j & 1);
             tc_fence_after();
             FA_FTR(0 + 4 * g)
-            issue_pv(g, tv, j > 0);
-            mma_commit(&o_done[g]);
+            issue_pv(g, tv, j > 0, 0);
+            mbar_wait(&p_hi[g], j & 1);
+            tc_fence_after();
+            issue_pv(g, tv, j > 0, 1);
+            commit(&o_done[g]);
             FA_FTR(1 + 4 * g)
             if (j + 1 < nkv[g]) {
               if (!k_ready) {
@@ -237,29 +266,30 @@ __global__ void __launch_bounds__(576, 1)
               }
               FA_FTR(2 + 4 * g)
               issue_qk(g, tk);
-              mma_commit(&s_full[g]);
+              commit(&s_full[g]);
               FA_FTR(3 + 4 * g)
             }
           }
         }
-        mma_commit(&kv_empty[tv % NSTAGE]);
-        if (j + 1 < nk) mma_commit(&kv_empty[tk % NSTAGE]);
+        commit(&kv_empty[tv % NSTAGE]);
+        if (j + 1 < nk) commit(&kv_empty[tk % NSTAGE]);
       }
     }
     __syncwarp();
    }
   } else {
     // ------------------------------------------------------------------ softmax groups
+    reg_alloc<104>();
     const int wg = warp >> 2, w = warp & 3;
     const int g = wg & 1, hh = wg >> 1;          // Q tile, column half
     const int rl = w * 32 + lane;                // row inside the tile == TMEM lane
     const int row = r0[g] + rl;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
     const uint32_t tSg = lane_base + (g ? Cfg::S_COL1 : Cfg::S_COL0);
-    // A thread owns 2 x 32 score columns of its row: chunk A = keys [32hh, 32hh+32) (columns the
-    // packed P will overwrite) and chunk B = keys [64+32hh, 96+32hh) (columns nobody overwrites before
-    // the next QK^T, so chunk B can be dropped after the max pass and re-read for the exp pass: only
-    // 32 scores are ever live in registers).
+    // A thread owns 2 x 32 score columns of its row: chunk A = keys [32hh, 32hh+32) and chunk B = keys
+    // [64+32hh, 96+32hh).  Both are loaded up front (64 live scores); the chunk-A exponentials of the two
+    // halves complete keys [0,64) of P, which is signalled separately (p_lo) so that half of P.V runs on
+    // the tensor pipe while the chunk-B exponentials are still being evaluated.
     const uint32_t tA = tSg + 32 * hh, tB = tSg + 64 + 32 * hh;
     const uint32_t tPA = tSg + 16 * hh, tPB = tSg + 32 + 16 * hh;   // packed P columns of chunk A / B
     const uint32_t tO = lane_base + (g ? Cfg::O_COL1 : Cfg::O_COL0) + (D / 2) * hh;
@@ -286,10 +316,9 @@ __global__ void __launch_bounds__(576, 1)
       }
     } else {
       float m_used = -INFINITY, m_true = -INFINITY, l_run = 0.f;
-      // 32 scores of my row starting at key `key0` -> registers, masks applied
-      auto load_chunk = [&](uint32_t taddr, int key0, float(&s)[32]) {
-        tmem_ld32f(taddr, s);
-        tmem_wait_ld();
+      // masks for the 32 scores of my row starting at key `key0` (generic additive mask, ragged / padded
+      // keys, causal diagonal tile)
+      auto mask_chunk = [&](int key0, float(&s)[32]) {
         if (MASKMODE == 2) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -305,61 +334,77 @@ __global__ void __launch_bounds__(576, 1)
             if (i >= limit) s[i] = -INFINITY;
         }
       };
-      auto max32 = [](const float(&s)[32]) {
-        float a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3];
+      auto max32 = [](const float(&s)[32]) {   // 16 FMNMX3 in four chains
+        float a0 = fmax3(s[0], s[1], s[2]), a1 = fmax3(s[3], s[4], s[5]);
+        float a2 = fmax3(s[6], s[7], s[8]), a3 = fmax3(s[9], s[10], s[11]);
 #pragma unroll
-        for (int i = 4; i < 32; i += 4) {
-          a0 = fmaxf(a0, s[i]), a1 = fmaxf(a1, s[i + 1]), a2 = fmaxf(a2, s[i + 2]), a3 = fmaxf(a3, s[i + 3]);
+        for (int i = 12; i < 28; i += 8) {
+          a0 = fmax3(a0, s[i], s[i + 1]), a1 = fmax3(a1, s[i + 2], s[i + 3]);
+          a2 = fmax3(a2, s[i + 4], s[i + 5]), a3 = fmax3(a3, s[i + 6], s[i + 7]);
         }
-        return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        return fmaxf(fmax3(a0, a1, s[28]), fmax3(a2, a3, fmax3(s[29], s[30], s[31])));
       };
-      // exp2 of 32 scores -> 16 packed bf16x2 registers, returns their sum.  Of every 8 exponentials
-      // EMU are evaluated by ex2_poly on the FMA pipe, the rest by MUFU.EX2 (see ptx.cuh).
+      // exp2 of 32 scores -> 16 packed bf16x2 registers, returns their sum.  x = s*sc - m*sc and the row sum
+      // are evaluated two columns per instruction (FFMA2 / FADD2).  Of every 8 exponentials EMU are evaluated
+      // by ex2_poly on the FMA pipe, the rest by MUFU.EX2 (see ptx.cuh).
       auto exp_pack = [&](const float(&s)[32], float neg_m, uint32_t(&pk)[16]) {
-        float r0_ = 0.f, r1_ = 0.f, r2_ = 0.f, r3_ = 0.f;
+        const uint64_t sc2 = f32x2(sc, sc), nm2 = f32x2(neg_m, neg_m);
+        uint64_t ra = f32x2(0.f, 0.f), rb = ra;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           float e[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const float x = fmaf(s[i + t], sc, neg_m);
-            const bool emu = (EMU >= 1 && t == 7) || (EMU >= 2 && t == 3) || (EMU >= 3 && t == 5) ||
-                             (EMU >= 4 && t == 1);
-            e[t] = emu ? ex2_poly(x) : ex2_approx(x);
+          for (int t = 0; t < 8; t += 2) {
+            float x0, x1;
+            f32x2_unpack(fma_f32x2(f32x2(s[i + t], s[i + t + 1]), sc2, nm2), x0, x1);
+            const bool emu0 = (EMU >= 2 && t == 2) || (EMU >= 4 && t == 6);
+            const bool emu1 = (EMU >= 1 && t == 6) || (EMU >= 3 && t == 4);
+            e[t] = emu0 ? ex2_poly(x0) : ex2_approx(x0);
+            e[t + 1] = emu1 ? ex2_poly(x1) : ex2_approx(x1);
           }
-          r0_ += e[0] + e[4], r1_ += e[1] + e[5], r2_ += e[2] + e[6], r3_ += e[3] + e[7];
+          ra = add_f32x2(ra, add_f32x2(f32x2(e[0], e[1]), f32x2(e[4], e[5])));
+          rb = add_f32x2(rb, add_f32x2(f32x2(e[2], e[3]), f32x2(e[6], e[7])));
 #pragma unroll
           for (int t = 0; t < 4; ++t) pk[i / 2 + t] = pack_bf16x2(e[2 * t], e[2 * t + 1]);
         }
-        return (r0_ + r1_) + (r2_ + r3_);
+        float s0, s1;
+        f32x2_unpack(add_f32x2(ra, rb), s0, s1);
+        return s0 + s1;
       };
       for (int j = 0; j < nkv[g]; ++j) {
         mbar_wait(&s_full[g], j & 1);
         tc_fence_after();
         FA_FTR(8 + 4 * wg)
         const int kA = j * 128 + 32 * hh, kB = kA + 64;
-        float mx;
-        {
-          float sB[32];
-          load_chunk(tB, kB, sB);
-          mx = max32(sB);
-        }
-        float sA[32];
-        load_chunk(tA, kA, sA);
-        mx = fmaxf(mx, max32(sA));
+        float sA[32], sB[32];
+        tmem_ld32f(tA, sA);      // both chunks in flight, one wait: 64 scores live
+        tmem_ld32f(tB, sB);
+        tmem_wait_ld();
+        mask_chunk(kA, sA);
+        mask_chunk(kB, sB);
+        float mx = fmaxf(max32(sA), max32(sB));
         x_mine[(j & 1) * 512] = mx;
         FA_FTR(9 + 4 * wg)
-        named_bar_sync(1 + g, 256);   // both halves hold their chunk A (P may overwrite it) and published
+        // Speculate that the reference maximum m_used survives this tile (it does unless some row maximum
+        // grows by more than 2^8): the chunk-A exponentials start right away on the MUFU pipe, the row-max
+        // reduction above shares their shadow on the ALU pipe, and the exchange with the other half of the
+        // row happens after them, when the partner has long arrived.  (j == 0 always takes the redo path.)
+        float neg_m = -m_used * sc;
+        uint32_t pk[16];
+        FA_FTR(28 + wg)
+        float sumA = exp_pack(sA, neg_m, pk);
+        pin16(pk, sumA);              // keep the speculative work ahead of the barrier
+        named_bar_sync(1 + g, 256);   // both halves hold their scores in registers (P may overwrite S) and published
         FA_FTR(10 + 4 * wg)
         mx = fmaxf(mx, x_peer[(j & 1) * 512]);
         m_true = fmaxf(m_true, mx);
-        if (j == 0) {
-          m_used = (mx == -INFINITY) ? 0.f : mx;
-        } else {
-          // lazy rescale: only when some row of this warp grew by more than 2^8.  The partner warp of
-          // the other half sees the same 32 row maxima, so both take the same decision.
-          const bool want = (mx - m_used) * sc > 8.0f;
-          if (__any_sync(0xffffffffu, want)) {
+        // lazy rescale: only when some row of this warp grew by more than 2^8.  The partner warp of the
+        // other half sees the same 32 row maxima, so both take the same decision.
+        const bool want = (j == 0) || ((mx - m_used) * sc > 8.0f);
+        if (__any_sync(0xffffffffu, want)) {
+          if (j == 0) {
+            m_used = (mx == -INFINITY) ? 0.f : mx;
+          } else {
             const float m_new = fmaxf(m_used, mx);
             const float factor = ex2_approx((m_used - m_new) * sc);
             m_used = m_new;
@@ -376,20 +421,28 @@ __global__ void __launch_bounds__(576, 1)
               tmem_st8(tO + 8 * c, u);
             }
           }
+          neg_m = -m_used * sc;
+          // redo chunk A against the new reference.  Its scores are re-read from TMEM (keeping them live
+          // across the speculative pass would cost 32 registers); nobody has stored P yet, and the extra
+          // barrier keeps the partner's P store behind this load.
+          tmem_ld32f(tA, sA);
+          tmem_wait_ld();
+          mask_chunk(kA, sA);
+          named_bar_sync(1 + g, 256);
+          sumA = exp_pack(sA, neg_m, pk);
         }
-        const float neg_m = -m_used * sc;
-        uint32_t pk[16];
-        l_run += exp_pack(sA, neg_m, pk);
+        l_run += sumA;
         tmem_st16(tPA, pk);
-        {
-          float sB[32];
-          load_chunk(tB, kB, sB);   // re-read: cheaper than keeping 32 more registers live
-          l_run += exp_pack(sB, neg_m, pk);
-        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_lo[g]);      // keys [0,64) of P are in TMEM: the first half of P.V may start
+        FA_FTR(24 + wg)
+        asm volatile("" : "+f"(neg_m));   // chunk B's exponentials stay behind the p_lo signal
+        l_run += exp_pack(sB, neg_m, pk);
         tmem_st16(tPB, pk);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[g]);
+        mbar_arrive(&p_hi[g]);
         FA_FTR(11 + 4 * wg)
       }
       // epilogue: combine the two halves' row sums, O / l -> global, statistics

@@ -181,6 +181,29 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors passed as (low word, high word): the high word of a descriptor is a
+// per-operand constant and the low word is `base + (byte offset >> 4)`, so stepping through the K
+// slices of a tile costs one integer add per operand instead of rebuilding the 64-bit descriptor.
+__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued tcgen05.mma of this thread arrive (count 1) on `bar` when complete.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -269,6 +292,31 @@ __device__ __forceinline__ float ex2_poly(float x) {
   pl = fmaf(pl, f, 0.6932609677f);
   pl = fmaf(pl, f, 0.9999280572f);
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 take one issue slot for two lanes' worth of work)
+// and the three-input maximum (FMNMX3).
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

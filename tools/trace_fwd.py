@@ -39,12 +39,10 @@ print("MMA issuer (per KV tile j): wait-satisfied / issue-done stamps, clk relat
 print(" j  " + " ".join(f"{n:>8s}" for n in mma))
 for j in range(4, 14):
     print(f"{j:2d}  " + " ".join(f"{T[j, k] - t0:8d}" for k in range(8)))
-print("softmax groups (lane 0 of warp 0 of each): s_full seen, max published, barrier passed, P arrived")
+print("softmax groups (lane 0 of warp 0 of each): s_full seen, max published, barrier passed, exp start, P_lo arrived, P_hi arrived")
 for wg, name in enumerate(["g0 h0", "g1 h0", "g0 h1", "g1 h1"]):
     print(name)
     for j in range(4, 10):
-        print(f"  {j:2d}  " + " ".join(f"{T[j, 8 + 4 * wg + k] - t0:8d}" for k in range(4)))
-print("MMA: before/after wait_full(V); g0h0 per-warp P-arrive times")
-for j in range(4, 10):
-    print(f"  {j:2d}  " + " ".join(f"{T[j, k] - t0:8d}" for k in (16, 17, 24, 25, 26, 27)))
+        cols = [8 + 4 * wg, 9 + 4 * wg, 10 + 4 * wg, 28 + wg, 24 + wg, 11 + 4 * wg]
+        print(f"  {j:2d}  " + " ".join(f"{T[j, k] - t0:8d}" for k in cols))
 print("period per KV tile:", (T[12, 0] - T[4, 0]) / 8)
