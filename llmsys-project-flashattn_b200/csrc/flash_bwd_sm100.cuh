@@ -14,14 +14,22 @@
 // memory in ONE layout that serves both remaining GEMMs: K-major A for dK, MN-major A for dQ.
 // Row statistics LSE_i and D_i = rowsum(dO*O) come from a pre-pass (log2 domain, padded so
 // out-of-range queries get P = 0) and arrive per Q tile with the same TMA transaction.
-//   warps 0-3 / 4-7 : two compute groups that alternate Q tiles (ping-pong): exp2 -> P^T,
-//                     dS^T = P^T*(dP^T - D), then drain dQ_i: TMEM -> registers -> 128B-swizzled
-//                     staging box in shared memory -> cp.reduce.async.bulk.tensor (fp32 add) into
-//                     the dQ accumulator (LSU red.global tops out near 9 clk per warp instruction
-//                     on B200, far too slow for 64 KB per tile pair)
-//   warp 8          : TMA producer (K,V once; Q_i + LSE_i + D_i 2-stage ring; dO_i single stage)
-//   warp 9          : tcgen05.mma issuer + TMEM allocation
-//   warp 10         : issues the dQ TMA reductions and recycles the two staging boxes
+//   warps 0-15      : four compute warpgroups (g, hh).  The two groups g alternate Q tiles (ping-pong);
+//                     inside a group two threads share a key row (TMEM lane), hh picks 64 of the 128
+//                     query columns: exp2 -> P^T, dS^T = P^T*(dP^T - D), then drain half of dQ_i:
+//                     TMEM -> registers -> 128B-swizzled staging box in shared memory ->
+//                     cp.reduce.async.bulk.tensor (fp32 add) into the dQ accumulator (LSU red.global
+//                     tops out near 9 clk per warp instruction on B200, far too slow for 64 KB per
+//                     tile pair).  T_dP is shared by dP(i), dS(i) and dQ(i), so the chain
+//                     dP(i) -> dS(i) -> dQ(i) -> drain -> dP(i+1) is the critical cycle of the kernel;
+//                     two threads per row halve every compute link of it.  No exchange is needed
+//                     between the halves: the backward uses the saved LSE, and each thread keeps its
+//                     P^T inside its own S^T columns (the dV GEMM reads the two 32-column pieces).
+//   warp 16         : TMA producer (K,V once; Q_i + LSE_i + D_i 2-stage ring; dO_i single stage)
+//   warp 17         : tcgen05.mma issuer + TMEM allocation
+//   warp 18         : issues the dQ TMA reductions and recycles the two staging boxes
+//   (warp 19 idle: 20 warps launch with 96 registers; setmaxnreg moves the compute warpgroups to 104
+//    and the helper warpgroup to 64)
 // The tensor pipe executes in issue order, so single-buffered T_S / T_dP are enough: S^T(i+1)
 // is issued right after dV(i) and overlaps the other group's dS phase.
 // dQ is accumulated across KV-tile CTAs in fp32 (TMA add-reductions; summation order varies
@@ -35,7 +43,7 @@ namespace sm100 {
 struct BwdParams {
   int B, H, N, Npad;
   const int* kv_len;
-  const float* lse2;   // (B*H, Npad) log2-domain LSE; +inf for rows >= N
+  const float* lse2;   // (B*H, Npad) NEGATED log2-domain LSE (an FFMA2 addend); -inf for rows >= N
   const float* dvec;   // (B*H, Npad) D_i; 0 for rows >= N
   float* dq_acc;       // (B,H,N,D) fp32, zero-initialised
   void* dK;            // bf16 outputs with the strides below
@@ -71,10 +79,10 @@ struct BwdCfg {
   static constexpr int OFF_STG = OFF_DS + DS_BYTES;         // [2 groups]
   static constexpr int OFF_VEC = OFF_STG + 2 * STG_BYTES;
   static constexpr int OFF_BAR = OFF_VEC + VEC_BYTES;
-  static constexpr int SMEM_USED = OFF_BAR + 256;
+  static constexpr int SMEM_USED = OFF_BAR + 264;   // 32 mbarriers + the TMEM base slot
   static constexpr int SMEM_BYTES = (SMEM_USED + 1024 <= 232448) ? SMEM_USED + 1024 : 232448;
   static constexpr int T_S = 0, T_DP = 128, T_DV = 256, T_DK = 256 + D;
-  static constexpr int NTHREADS = 384;
+  static constexpr int NTHREADS = 640;
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -86,7 +94,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 // Pre-pass of the tensor-core backward: D_i = sum_x dO*O and LSE_i (log2 domain), rows padded to
-// Npad per (b,h) with +inf / 0 so that out-of-range queries contribute P = 0; the same kernel
+// Npad per (b,h) with -inf (the LSE is stored negated) / 0 so that out-of-range queries contribute P = 0; the same kernel
 // zero-fills the fp32 dQ accumulator (saves a separate memset pass).  16 lanes x 16 bytes cover one
 // 128-element row, so every load is a full 128-bit coalesced access.
 template <int D>
@@ -122,10 +130,10 @@ __global__ void __launch_bounds__(256)
       if (n < N) {
         const long long sr = bh * N + n;
         const float l = L[sr];
-        lse2[r] = (l > 0.f) ? (M[sr] + logf(l)) * 1.4426950408889634f : INFINITY;
+        lse2[r] = (l > 0.f) ? -(M[sr] + logf(l)) * 1.4426950408889634f : -INFINITY;
         dvec[r] = s;
       } else {
-        lse2[r] = INFINITY;
+        lse2[r] = -INFINITY;
         dvec[r] = 0.f;
       }
     }
@@ -153,24 +161,6 @@ __global__ void bwd_convert_dq_kernel(int H, int N, int D, long long sb, long lo
   }
 }
 
-// exp2 of one 4-column group -> two packed bf16x2 registers
-#define FA_BWD_P4(c4, MASKED)                                                              \
-  {                                                                                        \
-    const float4 l4 = *reinterpret_cast<const float4*>(lse + 4 * (c4));                    \
-    float e0 = ex2_approx(fmaf(s[4 * (c4) + 0], p.scale_log2, -l4.x));                     \
-    float e1 = ex2_approx(fmaf(s[4 * (c4) + 1], p.scale_log2, -l4.y));                     \
-    float e2 = ex2_approx(fmaf(s[4 * (c4) + 2], p.scale_log2, -l4.z));                     \
-    float e3 = ex2_approx(fmaf(s[4 * (c4) + 3], p.scale_log2, -l4.w));                     \
-    if (MASKED) {                                                                          \
-      if (!key_ok || 4 * (c4) + 0 < cmin) e0 = 0.f;                                        \
-      if (!key_ok || 4 * (c4) + 1 < cmin) e1 = 0.f;                                        \
-      if (!key_ok || 4 * (c4) + 2 < cmin) e2 = 0.f;                                        \
-      if (!key_ok || 4 * (c4) + 3 < cmin) e3 = 0.f;                                        \
-    }                                                                                      \
-    pk[2 * (c4)] = pack_bf16x2(e0, e1);                                                    \
-    pk[2 * (c4) + 1] = pack_bf16x2(e2, e3);                                                \
-  }
-
 __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -178,7 +168,7 @@ __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
 }
 
 template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
     bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                const __grid_constant__ CUtensorMap tmdQ, const BwdParams p) {
@@ -212,8 +202,8 @@ __global__ void __launch_bounds__(384, 1)
   uint64_t* dq_free = bars + 19;     // [2]
   uint64_t* dkv_done = bars + 21;    // [1]
   uint64_t* stg_full = bars + 22;    // [2 buffers]        staging box written by a compute group
-  uint64_t* stg_empty = bars + 24;   // [2 groups][2 buf]  staging box read by the TMA reduction
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* stg_empty = bars + 24;   // [2 groups][2 halves][2 buf]  staging box read by the TMA reduction
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -242,7 +232,7 @@ __global__ void __launch_bounds__(384, 1)
     return;
   }
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -256,27 +246,26 @@ __global__ void __launch_bounds__(384, 1)
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
       mbar_init(&dp_full[i], 1);
-      mbar_init(&ds_full[i], 128);
+      mbar_init(&ds_full[i], 256);
       mbar_init(&ds_empty[i], 1);
       mbar_init(&dq_full[i], 1);
-      mbar_init(&dq_free[i], 128);
+      mbar_init(&dq_free[i], 256);
       mbar_init(&stg_full[i], 128);
-      mbar_init(&stg_empty[i], 1);
-      mbar_init(&stg_empty[2 + i], 1);
+      for (int k = 0; k < 4; ++k) mbar_init(&stg_empty[2 * k + i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
-    reg_dealloc<88>();
-    if (warp == 8) {
+  if (warp >= 16) {
+    reg_dealloc<64>();
+    if (warp == 16) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
         mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
@@ -304,7 +293,7 @@ __global__ void __launch_bounds__(384, 1)
         }
       }
       __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 17) {
       // ---------------------------------------------------------------- MMA issuer
       // The whole warp walks the schedule (uniform control flow keeps the descriptors in uniform
       // registers: no per-lane serialisation loop around every tcgen05.mma); one elected lane issues.
@@ -349,14 +338,16 @@ __global__ void __launch_bounds__(384, 1)
         for (int it = 0; it < n_iter; ++it) {
           const int s = it & 1, ph = (it >> 1) & 1;
           const uint32_t mQ = mn_lo(sQ + s * Cfg::TILE_BYTES);
-          // dV += P^T dO_i : A = P^T in TMEM (bf16, 8 columns per 16 queries), B = dO_i as [K=q][N=d]
+          // dV += P^T dO_i : A = P^T in TMEM (bf16, 8 columns per 16 queries; queries [0,64) sit in columns
+          // [0,32) and queries [64,128) in columns [64,96) of T_S), B = dO_i as [K=q][N=d]
           mbar_wait(&p_full[s], ph);
           tc_fence_after();
           FA_TR(0)
           if (leader) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              mma_ts2(tdV, tS + k * 8, mdO + k * (2048 >> 4), mn_hi, idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+              mma_ts2(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, mdO + k * (2048 >> 4), mn_hi, idesc_kn,
+                      (it > 0 || k > 0) ? 1u : 0u);
           }
           commit(do_empty);   // dO_i is dead once dV(i) has run (dP(i) ran earlier)
           FA_TR(1)
@@ -403,14 +394,14 @@ __global__ void __launch_bounds__(384, 1)
         commit(dkv_done);
       }
       __syncwarp();
-    } else if (warp == 10) {
+    } else if (warp == 18) {
       // ---------------------------------------------------------------- dQ reduction issuer
       // Rounds (it, c): the compute group of iteration `it` fills staging buffer c&1 with columns
       // [32c, 32c+32) of dQ_it; this thread turns each into one TMA add-reduction and hands the
       // buffer back (to whichever group uses it two rounds later) once the TMA has read it.
       if (lane == 0) {
-        constexpr int NR = D / 32;
-        int prev_g = 0, prev_b = 0;
+        constexpr int NR = D / 32, PER_WG = D / 64;   // rounds per iteration, boxes per warpgroup
+        int prev_slot = 0;
         bool have_prev = false;
         for (int it = 0; it < n_iter; ++it) {
           const int q0 = (q_first + it) * 128;
@@ -421,11 +412,13 @@ __global__ void __launch_bounds__(384, 1)
             tma_store_commit();
             if (have_prev) {
               tma_store_wait_read<1>();                       // the previous round's box has been read
-              mbar_arrive(&stg_empty[2 * prev_g + prev_b]);
+              mbar_arrive(&stg_empty[prev_slot]);
             }
-            // next user of this buffer: same iteration if c+2 < NR, otherwise the other group
-            prev_g = (c + 2 < NR) ? (it & 1) : ((it + 1) & 1);
-            prev_b = bsel;
+            // next user of this buffer: round c+2 of the same iteration if there is one, otherwise round
+            // c&1 of the next iteration (other group); each (group, half, buffer) has its own barrier
+            const int ng = (c + 2 < NR) ? (it & 1) : ((it + 1) & 1);
+            const int nc = (c + 2 < NR) ? (c + 2) : (c & 1);
+            prev_slot = (ng * 2 + nc / PER_WG) * 2 + bsel;
             have_prev = true;
           }
         }
@@ -434,55 +427,65 @@ __global__ void __launch_bounds__(384, 1)
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ compute groups
-    reg_alloc<208>();
-    const int g = warp >> 2, w = warp & 3;
+    // ------------------------------------------------------------------ compute warpgroups
+    reg_alloc<104>();
+    const int wg = warp >> 2, w = warp & 3;
+    const int g = wg & 1, hh = wg >> 1;          // Q-tile parity group, query-column half
     const int j = w * 32 + lane;                 // this thread's TMEM lane: key row (S^T, dP^T) / query row (dQ)
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
-    const uint32_t tS = lane_base + Cfg::T_S, tdP = lane_base + Cfg::T_DP;
+    const uint32_t tS = lane_base + Cfg::T_S + 64 * hh;         // my 64 S^T columns; my P^T = the first 32 of them
+    const uint32_t tdP = lane_base + Cfg::T_DP + 64 * hh;       // my 64 dP^T columns
+    const uint32_t tdQ = lane_base + Cfg::T_DP + (D / 2) * hh;  // my D/2 dQ columns
     const bool key_ok = (k0 + j) < kv_end;
     const bool all_keys_ok = (k0 + 128) <= kv_end;
-    uint8_t* ds_row = sdS + j * 128;
+    uint8_t* ds_row = sdS + hh * Cfg::CHUNK_BYTES + j * 128;    // my 64 queries = one 128-byte swizzled row
     uint8_t* stg_row = sStg + j * 128;
     const int jx = j & 7;
+    const uint64_t sc2 = f32x2(p.scale_log2, p.scale_log2);
 #ifdef FA_TRACE
-    long long* trw = tr;   // lane 0 of every warp of the group
-    if (w != 0) tr = nullptr;
+    long long* trw = (hh == 0) ? tr : nullptr;   // lane 0 of every warp of the hh = 0 warpgroups
+    if (w != 0 || hh != 0) tr = nullptr;
 #endif
 
     for (int it = g; it < n_iter; it += 2) {
       const int ph = (it >> 1) & 1;
       const int q0 = (q_first + it) * 128;
-      const float* lse = sVec + g * 256;
-      const float* dv = lse + 128;
+      const float* nlse = sVec + g * 256 + 64 * hh;   // -LSE2 of my 64 queries
+      const float* dv = sVec + g * 256 + 128 + 64 * hh;
       // ---- P^T = exp2(S^T * scale*log2e - LSE2[q])
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
       FA_TR(8)
       FA_TRW(2)
-      float s[128];
+      uint32_t pk[32];
+      {
+        float s[64];
+        tmem_ld32f(tS, &s[0]);
+        tmem_ld32f(tS + 32, &s[32]);
+        tmem_wait_ld();
+        FA_TR(9)
+        mbar_wait(&q_full[g], ph);  // LSE / D vectors of this Q tile are in shared memory
+        const bool diag = CAUSAL && (q0 < k0 + 128);
+        const int cmin = CAUSAL ? (k0 + j - q0 - 64 * hh) : 0;  // causal: my queries with index < cmin precede the key
+        const bool masked = !(all_keys_ok && !diag);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t u[32];
-        tmem_ld32(tS + 32 * c, u);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s[32 * c + i] = __uint_as_float(u[i]);
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(nlse + 4 * c4);
+          float x0, x1, x2, x3;
+          f32x2_unpack(fma_f32x2(f32x2(s[4 * c4], s[4 * c4 + 1]), sc2, f32x2(l4.x, l4.y)), x0, x1);
+          f32x2_unpack(fma_f32x2(f32x2(s[4 * c4 + 2], s[4 * c4 + 3]), sc2, f32x2(l4.z, l4.w)), x2, x3);
+          float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
+          if (masked) {
+            if (!key_ok || 4 * c4 + 0 < cmin) e0 = 0.f;
+            if (!key_ok || 4 * c4 + 1 < cmin) e1 = 0.f;
+            if (!key_ok || 4 * c4 + 2 < cmin) e2 = 0.f;
+            if (!key_ok || 4 * c4 + 3 < cmin) e3 = 0.f;
+          }
+          pk[2 * c4] = pack_bf16x2(e0, e1);
+          pk[2 * c4 + 1] = pack_bf16x2(e2, e3);
+        }
       }
-      tmem_wait_ld();
-      FA_TR(9)
-      mbar_wait(&q_full[g], ph);  // LSE / D vectors of this Q tile are in shared memory
-      uint32_t pk[64];
-      const bool diag = CAUSAL && (q0 < k0 + 128);
-      const int cmin = CAUSAL ? (k0 + j - q0) : 0;  // causal: queries q0+c < key are masked
-      if (all_keys_ok && !diag) {
-#pragma unroll
-        for (int c4 = 0; c4 < 32; ++c4) FA_BWD_P4(c4, false)
-      } else {
-#pragma unroll
-        for (int c4 = 0; c4 < 32; ++c4) FA_BWD_P4(c4, true)
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_st32(tS + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&pk[32 * c]));
+      tmem_st32(tS, pk);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
@@ -495,71 +498,73 @@ __global__ void __launch_bounds__(384, 1)
       FA_TR(11)
       FA_TRW(3)
       if (it >= 1) mbar_wait(&ds_empty[g ^ 1], ((it - 1) >> 1) & 1);  // dK(it-1) done with the buffer
-      uint32_t ua[2][32];
-      tmem_ld32(tdP, ua[0]);
+      uint32_t ua[2][16];
+      tmem_ld16(tdP, ua[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        tmem_wait_ld();                                         // chunk c is in registers
-        if (c < 3) tmem_ld32(tdP + 32 * (c + 1), ua[(c + 1) & 1]);  // prefetch the next 32 columns
-        if (c == 3) tc_fence_before();
-        const uint32_t(&u)[32] = ua[c & 1];
+        tmem_wait_ld();                                          // 16-column piece c is in registers
+        if (c < 3) tmem_ld16(tdP + 16 * (c + 1), ua[(c + 1) & 1]);   // prefetch the next piece
+        const uint32_t(&u)[16] = ua[c & 1];
 #pragma unroll
-        for (int v8 = 0; v8 < 4; ++v8) {   // 8 queries -> one 16-byte piece
-          const float4 da = *reinterpret_cast<const float4*>(dv + 32 * c + 8 * v8);
-          const float4 db = *reinterpret_cast<const float4*>(dv + 32 * c + 8 * v8 + 4);
+        for (int v8 = 0; v8 < 2; ++v8) {   // 8 queries -> one 16-byte piece
+          const float4 da = *reinterpret_cast<const float4*>(dv + 16 * c + 8 * v8);
+          const float4 db = *reinterpret_cast<const float4*>(dv + 16 * c + 8 * v8 + 4);
           uint4 o;
-          o.x = bf16x2_mul(pk[16 * c + 4 * v8 + 0], pack_bf16x2(__uint_as_float(u[8 * v8 + 0]) - da.x,
-                                                                __uint_as_float(u[8 * v8 + 1]) - da.y));
-          o.y = bf16x2_mul(pk[16 * c + 4 * v8 + 1], pack_bf16x2(__uint_as_float(u[8 * v8 + 2]) - da.z,
-                                                                __uint_as_float(u[8 * v8 + 3]) - da.w));
-          o.z = bf16x2_mul(pk[16 * c + 4 * v8 + 2], pack_bf16x2(__uint_as_float(u[8 * v8 + 4]) - db.x,
-                                                                __uint_as_float(u[8 * v8 + 5]) - db.y));
-          o.w = bf16x2_mul(pk[16 * c + 4 * v8 + 3], pack_bf16x2(__uint_as_float(u[8 * v8 + 6]) - db.z,
-                                                                __uint_as_float(u[8 * v8 + 7]) - db.w));
-          const int unit = 4 * (c & 1) + v8;  // 16-byte unit inside the 128-byte row of this chunk
-          *reinterpret_cast<uint4*>(ds_row + (c >> 1) * Cfg::CHUNK_BYTES + ((unit ^ jx) << 4)) = o;
+          o.x = bf16x2_mul(pk[8 * c + 4 * v8 + 0], pack_bf16x2(__uint_as_float(u[8 * v8 + 0]) - da.x,
+                                                               __uint_as_float(u[8 * v8 + 1]) - da.y));
+          o.y = bf16x2_mul(pk[8 * c + 4 * v8 + 1], pack_bf16x2(__uint_as_float(u[8 * v8 + 2]) - da.z,
+                                                               __uint_as_float(u[8 * v8 + 3]) - da.w));
+          o.z = bf16x2_mul(pk[8 * c + 4 * v8 + 2], pack_bf16x2(__uint_as_float(u[8 * v8 + 4]) - db.x,
+                                                               __uint_as_float(u[8 * v8 + 5]) - db.y));
+          o.w = bf16x2_mul(pk[8 * c + 4 * v8 + 3], pack_bf16x2(__uint_as_float(u[8 * v8 + 6]) - db.z,
+                                                               __uint_as_float(u[8 * v8 + 7]) - db.w));
+          const int unit = 2 * c + v8;  // 16-byte unit inside my 128-byte row
+          *reinterpret_cast<uint4*>(ds_row + ((unit ^ jx) << 4)) = o;
         }
       }
+      tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[g]);
       FA_TR(12)
       FA_TRW(1)
 
-      // ---- drain dQ_i (lane = query row): TMEM -> registers -> swizzled staging box -> TMA add-reduce
+      // ---- drain my half of dQ_i (lane = query row): TMEM -> registers -> swizzled staging box -> TMA add-reduce
       mbar_wait(&dq_full[g], ph);
       tc_fence_after();
       FA_TR(13)
-      uint32_t dq[D / 32][32];
+      uint32_t dq[D / 64][32];
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) tmem_ld32(tdP + 32 * c, dq[c]);
+      for (int c2 = 0; c2 < D / 64; ++c2) tmem_ld32(tdQ + 32 * c2, dq[c2]);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&dq_free[g]);          // T_dP may be overwritten by dP(it+1)
       FA_TR(14)
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        // use number u of buffer c&1 by THIS group; group 0's very first use finds the buffer free
-        const int u = (it >> 1) * (D / 64) + (c >> 1);
-        mbar_wait(&stg_empty[2 * g + (c & 1)], g == 0 ? ((u & 1) ^ 1) : (u & 1));
+      for (int c2 = 0; c2 < D / 64; ++c2) {
+        const int c = (D / 64) * hh + c2;   // 32-column box index inside dQ_i
+        // use number it>>1 of buffer c&1 by THIS warpgroup; the very first use of each buffer (rounds 0 and 1
+        // of iteration 0) finds it free
+        const int u = it >> 1;
+        mbar_wait(&stg_empty[(g * 2 + hh) * 2 + (c & 1)], (g == 0 && c < 2) ? ((u & 1) ^ 1) : (u & 1));
         uint8_t* dst = stg_row + (c & 1) * Cfg::STG_BYTES;
 #pragma unroll
         for (int u8 = 0; u8 < 8; ++u8)
           *reinterpret_cast<uint4*>(dst + ((u8 ^ jx) << 4)) =
-              make_uint4(dq[c][4 * u8], dq[c][4 * u8 + 1], dq[c][4 * u8 + 2], dq[c][4 * u8 + 3]);
+              make_uint4(dq[c2][4 * u8], dq[c2][4 * u8 + 1], dq[c2][4 * u8 + 2], dq[c2][4 * u8 + 3]);
         fence_proxy_async_smem();
         mbar_arrive(&stg_full[c & 1]);
       }
       FA_TR(15)
     }
 
-    // ---- epilogue: group 0 stores dK (scaled), group 1 stores dV
+    // ---- epilogue: group 0 stores dK (scaled), group 1 stores dV; each half stores D/2 columns
     mbar_wait(dkv_done, 0);
     tc_fence_after();
-    const uint32_t tacc = lane_base + (g == 0 ? Cfg::T_DK : Cfg::T_DV);
+    const uint32_t tacc = lane_base + (g == 0 ? Cfg::T_DK : Cfg::T_DV) + (D / 2) * hh;
     const float mul = (g == 0) ? p.scale : 1.0f;
-    __nv_bfloat16* orow = (g == 0 ? dKb : dVb) + static_cast<long long>(k0 + j) * p.sn;
+    __nv_bfloat16* orow = (g == 0 ? dKb : dVb) + static_cast<long long>(k0 + j) * p.sn + (D / 2) * hh;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < D / 64; ++c) {
       uint32_t u[32];
       tmem_ld32(tacc + 32 * c, u);
       tmem_wait_ld();
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(384, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace sm100

@@ -59,12 +59,6 @@ struct FwdCfg {
   static constexpr int NTHREADS = 640;
 };
 
-__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* r) {
-  uint32_t u[32];
-  tmem_ld32(taddr, u);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
-}
 
 template <typename OutT>
 __device__ __forceinline__ void store_row32(OutT* dst, const float* v);
