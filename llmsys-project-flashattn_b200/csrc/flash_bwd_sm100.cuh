@@ -27,9 +27,9 @@
 //                     P^T inside its own S^T columns (the dV GEMM reads the two 32-column pieces).
 //   warp 16         : TMA producer (K,V once; Q_i + LSE_i + D_i 2-stage ring; dO_i single stage)
 //   warp 17         : tcgen05.mma issuer + TMEM allocation
-//   warp 18         : issues the dQ TMA reductions and recycles the two staging boxes
-//   (warp 19 idle: 20 warps launch with 96 registers; setmaxnreg moves the compute warpgroups to 104
-//    and the helper warpgroup to 64)
+//   warps 18, 19    : issue the dQ TMA reductions of the hh = 0 / hh = 1 warpgroups, one staging box each
+//   (20 warps launch with 96 registers; setmaxnreg moves the compute warpgroups to 104 and the helper
+//    warpgroup to 64)
 // The tensor pipe executes in issue order, so single-buffered T_S / T_dP are enough: S^T(i+1)
 // is issued right after dV(i) and overlaps the other group's dS phase.
 // dQ is accumulated across KV-tile CTAs in fp32 (TMA add-reductions; summation order varies
@@ -79,7 +79,7 @@ struct BwdCfg {
   static constexpr int OFF_STG = OFF_DS + DS_BYTES;         // [2 groups]
   static constexpr int OFF_VEC = OFF_STG + 2 * STG_BYTES;
   static constexpr int OFF_BAR = OFF_VEC + VEC_BYTES;
-  static constexpr int SMEM_USED = OFF_BAR + 264;   // 32 mbarriers + the TMEM base slot
+  static constexpr int SMEM_USED = OFF_BAR + 256;
   static constexpr int SMEM_BYTES = (SMEM_USED + 1024 <= 232448) ? SMEM_USED + 1024 : 232448;
   static constexpr int T_S = 0, T_DP = 128, T_DV = 256, T_DK = 256 + D;
   static constexpr int NTHREADS = 640;
@@ -201,9 +201,9 @@ __global__ void __launch_bounds__(640, 1)
   uint64_t* dq_full = bars + 17;     // [2]
   uint64_t* dq_free = bars + 19;     // [2]
   uint64_t* dkv_done = bars + 21;    // [1]
-  uint64_t* stg_full = bars + 22;    // [2 buffers]        staging box written by a compute group
-  uint64_t* stg_empty = bars + 24;   // [2 groups][2 halves][2 buf]  staging box read by the TMA reduction
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint64_t* stg_full = bars + 22;    // [2 halves]            staging box hh written by warpgroup (g, hh)
+  uint64_t* stg_empty = bars + 24;   // [2 halves][2 groups]  staging box hh read by the TMA reduction, free for (g, hh)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(640, 1)
       mbar_init(&dq_full[i], 1);
       mbar_init(&dq_free[i], 256);
       mbar_init(&stg_full[i], 128);
-      for (int k = 0; k < 4; ++k) mbar_init(&stg_empty[2 * k + i], 1);
+      mbar_init(&stg_empty[i], 1);
+      mbar_init(&stg_empty[2 + i], 1);
     }
     fence_mbar_init();
   }
@@ -394,32 +395,23 @@ __global__ void __launch_bounds__(640, 1)
         commit(dkv_done);
       }
       __syncwarp();
-    } else if (warp == 18) {
-      // ---------------------------------------------------------------- dQ reduction issuer
-      // Rounds (it, c): the compute group of iteration `it` fills staging buffer c&1 with columns
-      // [32c, 32c+32) of dQ_it; this thread turns each into one TMA add-reduction and hands the
-      // buffer back (to whichever group uses it two rounds later) once the TMA has read it.
+    } else {
+      // ---------------------------------------------------------------- dQ reduction issuers (warps 18, 19)
+      // Warp 18 + hh serves the warpgroups (., hh): staging box hh receives columns [D/2*hh + 32*c2, +32) of
+      // dQ_it from warpgroup (it & 1, hh); one lane turns each fill into a TMA add-reduction and hands the
+      // box to its next user once the TMA has read it.  The two halves never wait for each other.
       if (lane == 0) {
-        constexpr int NR = D / 32, PER_WG = D / 64;   // rounds per iteration, boxes per warpgroup
-        int prev_slot = 0;
-        bool have_prev = false;
+        constexpr int PER_WG = D / 64;   // 32-column boxes per warpgroup and iteration
+        const int hh = warp - 18;
         for (int it = 0; it < n_iter; ++it) {
           const int q0 = (q_first + it) * 128;
-          for (int c = 0; c < NR; ++c) {
-            const int bsel = c & 1;
-            mbar_wait(&stg_full[bsel], ((it * (NR / 2) + (c >> 1)) & 1));
-            tma_reduce_add_4d(&tmdQ, sStg + bsel * Cfg::STG_BYTES, 32 * c, q0, h, b);
+          for (int c2 = 0; c2 < PER_WG; ++c2) {
+            mbar_wait(&stg_full[hh], (it * PER_WG + c2) & 1);
+            tma_reduce_add_4d(&tmdQ, sStg + hh * Cfg::STG_BYTES, (D / 2) * hh + 32 * c2, q0, h, b);
             tma_store_commit();
-            if (have_prev) {
-              tma_store_wait_read<1>();                       // the previous round's box has been read
-              mbar_arrive(&stg_empty[prev_slot]);
-            }
-            // next user of this buffer: round c+2 of the same iteration if there is one, otherwise round
-            // c&1 of the next iteration (other group); each (group, half, buffer) has its own barrier
-            const int ng = (c + 2 < NR) ? (it & 1) : ((it + 1) & 1);
-            const int nc = (c + 2 < NR) ? (c + 2) : (c & 1);
-            prev_slot = (ng * 2 + nc / PER_WG) * 2 + bsel;
-            have_prev = true;
+            tma_store_wait_read<0>();                         // the box has been read
+            // next user: the same warpgroup for its next box of this iteration, otherwise the other group
+            mbar_arrive(&stg_empty[2 * hh + ((c2 + 1 < PER_WG) ? (it & 1) : ((it + 1) & 1))]);
           }
         }
         tma_store_wait_all<0>();
@@ -541,18 +533,16 @@ __global__ void __launch_bounds__(640, 1)
       FA_TR(14)
 #pragma unroll
       for (int c2 = 0; c2 < D / 64; ++c2) {
-        const int c = (D / 64) * hh + c2;   // 32-column box index inside dQ_i
-        // use number it>>1 of buffer c&1 by THIS warpgroup; the very first use of each buffer (rounds 0 and 1
-        // of iteration 0) finds it free
-        const int u = it >> 1;
-        mbar_wait(&stg_empty[(g * 2 + hh) * 2 + (c & 1)], (g == 0 && c < 2) ? ((u & 1) ^ 1) : (u & 1));
-        uint8_t* dst = stg_row + (c & 1) * Cfg::STG_BYTES;
+        // use number u of staging box hh by THIS warpgroup; group 0's very first use finds the box free
+        const int u = (it >> 1) * (D / 64) + c2;
+        mbar_wait(&stg_empty[2 * hh + g], g == 0 ? ((u & 1) ^ 1) : (u & 1));
+        uint8_t* dst = stg_row + hh * Cfg::STG_BYTES;
 #pragma unroll
         for (int u8 = 0; u8 < 8; ++u8)
           *reinterpret_cast<uint4*>(dst + ((u8 ^ jx) << 4)) =
               make_uint4(dq[c2][4 * u8], dq[c2][4 * u8 + 1], dq[c2][4 * u8 + 2], dq[c2][4 * u8 + 3]);
         fence_proxy_async_smem();
-        mbar_arrive(&stg_full[c & 1]);
+        mbar_arrive(&stg_full[hh]);
       }
       FA_TR(15)
     }
