@@ -277,6 +277,9 @@ __global__ void __launch_bounds__(640, 1)
     const int wg = warp >> 2, w = warp & 3;
     const int g = wg & 1, hh = wg >> 1;          // Q tile, column half
     const int rl = w * 32 + lane;                // row inside the tile == TMEM lane
+    // The two warps that share 32 rows (column halves hh = 0 / 1) synchronise on their own named barrier:
+    // the rescale decision below is taken per warp, so anything wider could deadlock on divergent data.
+    const uint32_t pair_bar = 1 + g * 4 + w;
     const int row = r0[g] + rl;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
     const uint32_t tSg = lane_base + (g ? Cfg::S_COL1 : Cfg::S_COL0);
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(640, 1)
         FA_FTR(28 + wg)
         float sumA = exp_pack(sA, neg_m, pk);
         pin16(pk, sumA);              // keep the speculative work ahead of the barrier
-        named_bar_sync(1 + g, 256);   // both halves hold their scores in registers (P may overwrite S) and published
+        named_bar_sync(pair_bar, 64);   // both halves hold their scores in registers (P may overwrite S) and published
         FA_FTR(10 + 4 * wg)
         mx = fmaxf(mx, x_peer[(j & 1) * 512]);
         m_true = fmaxf(m_true, mx);
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(640, 1)
           tmem_ld32f(tA, sA);
           tmem_wait_ld();
           mask_chunk(kA, sA);
-          named_bar_sync(1 + g, 256);
+          named_bar_sync(pair_bar, 64);
           sumA = exp_pack(sA, neg_m, pk);
         }
         l_run += sumA;
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(640, 1)
       // epilogue: combine the two halves' row sums, O / l -> global, statistics
       const int par = nkv[g] & 1;
       x_mine[par * 512] = l_run;
-      named_bar_sync(1 + g, 256);
+      named_bar_sync(pair_bar, 64);
       const float l_tot = l_run + x_peer[par * 512];
       mbar_wait(&o_done[g], (nkv[g] - 1) & 1);
       tc_fence_after();

@@ -129,3 +129,49 @@ def test_bf16_reproducible_to_rounding():
     np.testing.assert_array_equal(runs[0][2], runs[1][2])
     np.testing.assert_array_equal(runs[0][3], runs[1][3])
     assert maxabs(runs[0][1], runs[1][1]) <= 2.0 ** -7 * max(1.0, float(np.abs(runs[0][1]).max()))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("d", [128, 64])
+@pytest.mark.parametrize("causal", [False, True])
+def test_bf16_lazy_rescale_divergent_rows(causal, d):
+    """Online-softmax rescale taken by SOME warps only: a few query rows meet a key whose score exceeds the
+    running maximum by far more than the lazy-rescale threshold (2^8) in a LATE key tile, the other rows
+    never do.  (The rescale decision is per warp; an earlier version synchronised it across the whole Q tile
+    and hung on exactly this pattern.)  Also covers rows whose maximum jumps in several different tiles."""
+    B, H, N = 1, 2, 640
+    rng = np.random.default_rng(77)
+    Q, K, V, dO = (rng.standard_normal((B, H, N, d)).astype(np.float32) for _ in range(4))
+    Q[..., 0] = 0.0
+    K[..., 0] = 0.0
+    # rows 0-31 (one warp of Q tile 0), 200-210 (part of a warp of tile 1) and 500-540 get a large component
+    for rows, key in (((0, 32), 300), ((200, 211), 420), ((500, 541), 600), ((5, 9), 639)):
+        Q[:, :, rows[0]:rows[1], 0] = 4.0
+        K[:, :, key, 0] = 40.0 if key != 639 else 80.0
+    Q, K, V, dO = (R.round_bf16(x) for x in (Q, K, V, dO))
+    dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(x, "bf16") for x in (Q, K, V, dO))
+    O, m, l = dev.flash_fwd(dq, dk, dv, causal=causal)
+    Oe, me, le = R.attention_fwd(Q, K, V, causal=causal)
+    assert maxabs(O.to_numpy(), Oe) < TOL
+    assert maxabs(m.to_numpy() + np.log(l.to_numpy()), me + np.log(le)) < 2e-3
+    gq, gk, gv = dev.flash_bwd(dq, dk, dv, O, ddo, m, l, causal=causal)
+    ge = R.attention_bwd(Q, K, V, dO, causal=causal)
+    # This data makes dQ[:, 0] a difference of large terms (two keys with |K[k, 0]| = 40 share a row's
+    # probability mass, dS_a = -dS_b), so the error bound has to follow the bf16 rounding of P and dS
+    # (2^-8 relative each) through the contraction: |d dQ| <= 2^-7 * scale * (|dS| @ |K|), and likewise
+    # for dK and dV.
+    Q64, K64, V64, dO64 = (x.astype(np.float64) for x in (Q, K, V, dO))
+    sc = 1.0 / np.sqrt(d)
+    S = np.einsum("bhqd,bhkd->bhqk", Q64, K64) * sc
+    if causal:
+        S = np.where(np.arange(N)[None, :] > np.arange(N)[:, None], -np.inf, S)
+    P = np.exp(S - S.max(-1, keepdims=True))
+    P /= P.sum(-1, keepdims=True)
+    dP = np.einsum("bhqd,bhkd->bhqk", dO64, V64)
+    dS = P * (dP - (P * dP).sum(-1, keepdims=True))
+    bounds = (2.0 ** -7 * sc * np.einsum("bhqk,bhkd->bhqd", np.abs(dS), np.abs(K64)),
+              2.0 ** -7 * sc * np.einsum("bhqk,bhqd->bhkd", np.abs(dS), np.abs(Q64)),
+              2.0 ** -7 * np.einsum("bhqk,bhqd->bhkd", P, np.abs(dO64)))
+    for got, want, bnd, name in zip((gq, gk, gv), ge, bounds, ("dQ", "dK", "dV")):
+        err = np.abs(got.to_numpy().astype(np.float64) - want)
+        assert np.all(err <= TOL + BF16_EPS * np.abs(want) + bnd), (name, float(err.max()))

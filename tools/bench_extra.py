@@ -137,6 +137,8 @@ def attn_case(P, B, H, N, d, causal, kv=None, bwd=False, reps=8):
         r["bwd_frac_sustained"] = r["bwd_tflops"] / P["tf_sustained"]
         r["bwd_frac_burst"] = r["bwd_tflops"] / P["tf_burst"]
         r["bwd_frac_datasheet"] = r["bwd_tflops"] / 2250.0
+    print("case", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if "frac" not in k},
+          file=sys.stderr, flush=True)
     return r
 
 

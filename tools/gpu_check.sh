@@ -16,6 +16,8 @@ for g in $groups; do
     combine) run combine python -m pytest tests/test_gpu_combine.py -q -m gpu ;;
     mha) run mha python -m pytest tests/test_gpu_mha_integration.py -q -m gpu ;;
     extra) run extra python tools/bench_extra.py --out gpurun_out/extra.json ;;
+    extra_attn) run extra_attn python tools/bench_extra.py --what sweep,cfg4 --out gpurun_out/extra_attn.json ;;
+    extra_comp) run extra_comp python tools/bench_extra.py --what companions --out gpurun_out/extra_comp.json ;;
     alltests) run alltests python -m pytest tests -x -q -m gpu ;;
     bench) run bench python bench.py --steps 10 --warmup 3 ;;
     benchq) run benchq python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu ;;
