@@ -63,6 +63,11 @@ enum { FA_DTYPE_F32 = 0, FA_DTYPE_BF16 = 1 };
 enum { FA_MODE_FP32 = 0, FA_MODE_BF16 = 1 };
 void fa_set_mode(int mode);
 int fa_get_mode(void);
+/* The legacy entry points are transfer-bound, so they cut the (batch, head) units into chunks of about
+ * this many bytes of fp32 per tensor and overlap H2D of chunk c+1, the kernels of chunk c and D2H of
+ * chunk c-1 on three streams (results are independent of the chunking).  Default 32 MiB, or env
+ * MINITORCH_FA_CHUNK_MB; 0 restores the default. */
+void fa_set_legacy_chunk_bytes(size_t bytes);
 
 /* Legacy ABI -- identical to the reference's
  *   src/flashattention_kernel.cu:259 launch_flashattention_forward

@@ -65,6 +65,7 @@ SYMBOLS = {
         **_COMMON,
         "fa_set_mode": (None, [c_int]),
         "fa_get_mode": (c_int, []),
+        "fa_set_legacy_chunk_bytes": (None, [c_size_t]),
         "launch_flashattention_forward": (None, _HOST4),
         "launch_flashattention_forward_causal": (None, _HOST4),
         "launch_flashattention_backward": (None, _HOST4B),

@@ -472,6 +472,69 @@ static int stage_mask(fa_attn_desc* a, const float* key_mask, int slot) {
   return FA_OK;
 }
 
+// The legacy calls are transfer-bound (cfg4: 6.4 GB over PCIe per fwd+bwd step against 7 ms of kernels), so
+// the (batch, head) units -- independent attention problems -- are cut into chunks that flow through three
+// streams: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 run concurrently (both copy directions
+// of the link are busy at once).  A chunk never straddles a batch, so kv_len / the key mask index by batch.
+struct LegacyPipe {
+  cudaStream_t in = nullptr, comp = nullptr, out = nullptr;
+  cudaEvent_t ev_in[256] = {}, ev_comp[256] = {};
+  int dev = -1;
+  int nev = 0;
+  int init() {
+    int d = 0;
+    FA_CUDA_CHECK(cudaGetDevice(&d));
+    if (dev == d && in) return FA_OK;
+    if (in) {  // device changed: the old device's streams stay alive (tiny), make new ones
+      in = comp = out = nullptr;
+      nev = 0;
+    }
+    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+    dev = d;
+    return FA_OK;
+  }
+  int events(int n) {
+    if (n > 256) return set_error(FA_ERR_INVALID, "legacy pipeline: too many chunks (%d)", n);
+    for (; nev < n; ++nev) {
+      FA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in[nev], cudaEventDisableTiming));
+      FA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_comp[nev], cudaEventDisableTiming));
+    }
+    return FA_OK;
+  }
+  int drain() {
+    cudaError_t e1 = cudaStreamSynchronize(in), e2 = cudaStreamSynchronize(comp), e3 = cudaStreamSynchronize(out);
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    if (e != cudaSuccess) return set_error(FA_ERR_CUDA, "legacy pipeline: %s", cudaGetErrorString(e));
+    return FA_OK;
+  }
+};
+static LegacyPipe g_pipe;
+
+struct Chunk {
+  int b, h0, hc;
+};
+// Heads per chunk: about kChunkBytes of fp32 per tensor, at most 256 chunks, whole heads only.
+static size_t g_chunk_bytes = 0;  // 0 = unresolved: env MINITORCH_FA_CHUNK_MB or 32 MiB
+static int plan_chunks(int B, int nh, int N, int d, Chunk* out, int cap) {
+  if (!g_chunk_bytes) {
+    const char* e = getenv("MINITORCH_FA_CHUNK_MB");
+    const long mb = e ? atol(e) : 32;
+    g_chunk_bytes = (size_t)(mb > 0 ? mb : 32) << 20;
+  }
+  const size_t chunk_bytes = g_chunk_bytes;
+  const size_t head_bytes = (size_t)N * d * 4;
+  int hc = (int)(chunk_bytes / head_bytes);
+  if (hc < 1) hc = 1;
+  if (hc > nh) hc = nh;
+  while ((size_t)B * ((nh + hc - 1) / hc) > (size_t)cap) ++hc;
+  int n = 0;
+  for (int b = 0; b < B; ++b)
+    for (int h0 = 0; h0 < nh; h0 += hc) out[n++] = Chunk{b, h0, (nh - h0 < hc) ? nh - h0 : hc};
+  return n;
+}
+
 static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, float* m, const float* key_mask,
                            int causal, int B, int nh, int N, int d) {
   clear_error();
@@ -490,63 +553,73 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
     return;
   }
   float *dm = dml, *dl = dml + r;
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) {
-    if (e == cudaSuccess) e = x;
-  };
-  step(cudaMemcpyAsync(dQ_, Q, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(dK_, K, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(dV_, V, n * 4, cudaMemcpyHostToDevice, 0));
-  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
-  if (e != cudaSuccess) {
-    set_error(FA_ERR_CUDA, "launch_flashattention_forward: H2D: %s", cudaGetErrorString(e));
-    return;
-  }
-  int rc;
-  if (current_mode() == FA_MODE_BF16 && (d == 64 || d == 128)) {
-    // round the operands to bf16 on device; the kernel writes fp32 O directly
-    __nv_bfloat16* bq = static_cast<__nv_bfloat16*>(g_pool.get(5, n * 2));
-    __nv_bfloat16* bk = static_cast<__nv_bfloat16*>(g_pool.get(6, n * 2));
-    __nv_bfloat16* bv = static_cast<__nv_bfloat16*>(g_pool.get(7, n * 2));
+  const bool tc = current_mode() == FA_MODE_BF16 && (d == 64 || d == 128);
+  __nv_bfloat16 *bq = nullptr, *bk = nullptr, *bv = nullptr;
+  if (tc) {  // round the operands to bf16 on device; the kernel writes fp32 O directly
+    bq = static_cast<__nv_bfloat16*>(g_pool.get(5, n * 2));
+    bk = static_cast<__nv_bfloat16*>(g_pool.get(6, n * 2));
+    bv = static_cast<__nv_bfloat16*>(g_pool.get(7, n * 2));
     if (!bq || !bk || !bv) {
       set_error(FA_ERR_CUDA, "launch_flashattention_forward: bf16 staging allocation failed");
       return;
     }
-    if (fa_cast_f32_to_bf16_dev(dQ_, bq, n, 0) || fa_cast_f32_to_bf16_dev(dK_, bk, n, 0) ||
-        fa_cast_f32_to_bf16_dev(dV_, bv, n, 0))
-      return;
-    a.dtype = FA_DTYPE_BF16;
-    rc = fwd_tc<float>(&a, bq, bk, bv, dO_, (long long)nh * N * d, (long long)N * d, d, dm, dl, 0);
-  } else {
-    rc = fa_flash_fwd_dev(&a, dQ_, dK_, dV_, dO_, dm, dl, 0);
   }
-  if (rc != FA_OK) return;
-  step(cudaMemcpyAsync(O, dO_, n * 4, cudaMemcpyDeviceToHost, 0));
-  step(cudaMemcpyAsync(m, dm, r * 4, cudaMemcpyDeviceToHost, 0));
-  step(cudaMemcpyAsync(l, dl, r * 4, cudaMemcpyDeviceToHost, 0));
-  step(cudaStreamSynchronize(0));
-  if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_forward: %s", cudaGetErrorString(e));
-}
-
-// bf16 mode of the legacy backward: round the fp32 operands to bf16 on device, run the bf16
-// backward, widen the gradients back to fp32 in place of the fp32 staging buffers.
-static int bwd_bf16_from_f32(fa_attn_desc* a, float* gQ, float* gK, float* gV, float* gO, float* gdO, const float* dm,
-                             const float* dl, float* gdQ, float* gdK, float* gdV) {
-  const size_t n = (size_t)a->B * a->H * a->N * a->d;
-  __nv_bfloat16* b[8];
-  for (int i = 0; i < 8; ++i) {
-    b[i] = static_cast<__nv_bfloat16*>(g_pool.get(16 + i, n * 2));
-    if (!b[i]) return set_error(FA_ERR_CUDA, "launch_flashattention_backward: bf16 staging allocation failed");
+  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
+  if (cudaStreamSynchronize(0) != cudaSuccess) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_forward: mask upload failed");
+    return;
   }
-  float* src[5] = {gQ, gK, gV, gO, gdO};
-  for (int i = 0; i < 5; ++i)
-    if (int rc = fa_cast_f32_to_bf16_dev(src[i], b[i], n, 0)) return rc;
-  a->dtype = FA_DTYPE_BF16;
-  if (int rc = fa_flash_bwd_dev(a, b[0], b[1], b[2], b[3], b[4], dm, dl, b[5], b[6], b[7], 0)) return rc;
-  float* dst[3] = {gdQ, gdK, gdV};
-  for (int i = 0; i < 3; ++i)
-    if (int rc = fa_cast_bf16_to_f32_dev(b[5 + i], dst[i], n, 0)) return rc;
-  return FA_OK;
+  static Chunk chunks[256];
+  const int nc = plan_chunks(B, nh, N, d, chunks, 256);
+  LegacyPipe& P = g_pipe;
+  if (P.init() != FA_OK || P.events(nc) != FA_OK) return;
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t x) {
+    if (e == cudaSuccess) e = x;
+  };
+  int rc = FA_OK;
+  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
+    const Chunk& ck = chunks[c];
+    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.hc * N * d;
+    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.hc * N;
+    step(cudaMemcpyAsync(dQ_ + off, Q + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+    step(cudaMemcpyAsync(dK_ + off, K + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+    step(cudaMemcpyAsync(dV_ + off, V + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+    step(cudaEventRecord(P.ev_in[c], P.in));
+    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
+    fa_attn_desc ca = a;
+    ca.B = 1, ca.H = ck.hc;
+    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
+    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
+    fa_stream_t cs = reinterpret_cast<fa_stream_t>(P.comp);
+    if (tc) {
+      if (fa_cast_f32_to_bf16_dev(dQ_ + off, bq + off, cn, cs) || fa_cast_f32_to_bf16_dev(dK_ + off, bk + off, cn, cs) ||
+          fa_cast_f32_to_bf16_dev(dV_ + off, bv + off, cn, cs)) {
+        rc = fa_last_status();
+        break;
+      }
+      ca.dtype = FA_DTYPE_BF16;
+      rc = fwd_tc<float>(&ca, bq + off, bk + off, bv + off, dO_ + off, (long long)ck.hc * N * d, (long long)N * d, d,
+                         dm + roff, dl + roff, P.comp);
+    } else {
+      rc = fa_flash_fwd_dev(&ca, dQ_ + off, dK_ + off, dV_ + off, dO_ + off, dm + roff, dl + roff, cs);
+    }
+    if (rc != FA_OK) break;
+    step(cudaEventRecord(P.ev_comp[c], P.comp));
+    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
+    step(cudaMemcpyAsync(O + off, dO_ + off, cn * 4, cudaMemcpyDeviceToHost, P.out));
+    step(cudaMemcpyAsync(m + roff, dm + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
+    step(cudaMemcpyAsync(l + roff, dl + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
+  }
+  // always drain: the caller owns the host buffers and may free them as soon as we return
+  const int saved = fa_last_status();
+  char saved_msg[512];
+  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
+  saved_msg[sizeof(saved_msg) - 1] = 0;
+  const int drc = P.drain();
+  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
+  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_forward: %s", cudaGetErrorString(e));
+  (void)drc;
 }
 
 static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV, float* dO,
@@ -571,38 +644,76 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
     return;
   }
   float *dm = dml, *dl = dml + r;
-  float *gQ = buf[0], *gK = buf[1], *gV = buf[2], *gO = buf[3], *gdO = buf[4], *gdQ = buf[5], *gdK = buf[6],
-        *gdV = buf[7];
+  const bool tc = current_mode() == FA_MODE_BF16 && (d == 64 || d == 128);
+  // bf16 mode: round the fp32 operands to bf16 on device, run the bf16 backward, widen the gradients
+  // back to fp32 into the fp32 staging buffers.
+  __nv_bfloat16* hb[8] = {};
+  if (tc)
+    for (int i = 0; i < 8; ++i) {
+      hb[i] = static_cast<__nv_bfloat16*>(g_pool.get(16 + i, n * 2));
+      if (!hb[i]) {
+        set_error(FA_ERR_CUDA, "launch_flashattention_backward: bf16 staging allocation failed");
+        return;
+      }
+    }
+  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
+  if (cudaStreamSynchronize(0) != cudaSuccess) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_backward: mask upload failed");
+    return;
+  }
+  static Chunk chunks[256];
+  const int nc = plan_chunks(B, nh, N, d, chunks, 256);
+  LegacyPipe& P = g_pipe;
+  if (P.init() != FA_OK || P.events(nc) != FA_OK) return;
+  float* const host_in[5] = {Q, K, V, O, dO};
+  float* const host_out[3] = {dQ, dK, dV};
   cudaError_t e = cudaSuccess;
   auto step = [&](cudaError_t x) {
     if (e == cudaSuccess) e = x;
   };
-  step(cudaMemcpyAsync(gQ, Q, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(gK, K, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(gV, V, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(gO, O, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(gdO, dO, n * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(dm, m, r * 4, cudaMemcpyHostToDevice, 0));
-  step(cudaMemcpyAsync(dl, l, r * 4, cudaMemcpyHostToDevice, 0));
-  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
-  if (e != cudaSuccess) {
-    set_error(FA_ERR_CUDA, "launch_flashattention_backward: H2D: %s", cudaGetErrorString(e));
-    return;
+  int rc = FA_OK;
+  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
+    const Chunk& ck = chunks[c];
+    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.hc * N * d;
+    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.hc * N;
+    for (int i = 0; i < 5; ++i)
+      step(cudaMemcpyAsync(buf[i] + off, host_in[i] + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+    step(cudaMemcpyAsync(dm + roff, m + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
+    step(cudaMemcpyAsync(dl + roff, l + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
+    step(cudaEventRecord(P.ev_in[c], P.in));
+    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
+    fa_attn_desc ca = a;
+    ca.B = 1, ca.H = ck.hc;
+    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
+    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
+    fa_stream_t cs = reinterpret_cast<fa_stream_t>(P.comp);
+    if (tc) {
+      for (int i = 0; i < 5 && rc == FA_OK; ++i) rc = fa_cast_f32_to_bf16_dev(buf[i] + off, hb[i] + off, cn, cs);
+      ca.dtype = FA_DTYPE_BF16;
+      if (rc == FA_OK)
+        rc = fa_flash_bwd_dev(&ca, hb[0] + off, hb[1] + off, hb[2] + off, hb[3] + off, hb[4] + off, dm + roff,
+                              dl + roff, hb[5] + off, hb[6] + off, hb[7] + off, cs);
+      for (int i = 0; i < 3 && rc == FA_OK; ++i) rc = fa_cast_bf16_to_f32_dev(hb[5 + i] + off, buf[5 + i] + off, cn, cs);
+    } else {
+      rc = fa_flash_bwd_dev(&ca, buf[0] + off, buf[1] + off, buf[2] + off, buf[3] + off, buf[4] + off, dm + roff,
+                            dl + roff, buf[5] + off, buf[6] + off, buf[7] + off, cs);
+    }
+    if (rc != FA_OK) break;
+    step(cudaEventRecord(P.ev_comp[c], P.comp));
+    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
+    for (int i = 0; i < 3; ++i)
+      step(cudaMemcpyAsync(host_out[i] + off, buf[5 + i] + off, cn * 4, cudaMemcpyDeviceToHost, P.out));
   }
-  int rc;
-  if (current_mode() == FA_MODE_BF16 && (d == 64 || d == 128)) {
-    rc = bwd_bf16_from_f32(&a, gQ, gK, gV, gO, gdO, dm, dl, gdQ, gdK, gdV);
-  } else {
-    rc = fa_flash_bwd_dev(&a, gQ, gK, gV, gO, gdO, dm, dl, gdQ, gdK, gdV, 0);
-  }
-  if (rc != FA_OK) return;
-  step(cudaMemcpyAsync(dQ, gdQ, n * 4, cudaMemcpyDeviceToHost, 0));
-  step(cudaMemcpyAsync(dK, gdK, n * 4, cudaMemcpyDeviceToHost, 0));
-  step(cudaMemcpyAsync(dV, gdV, n * 4, cudaMemcpyDeviceToHost, 0));
-  step(cudaStreamSynchronize(0));
-  if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
+  const int saved = fa_last_status();
+  char saved_msg[512];
+  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
+  saved_msg[sizeof(saved_msg) - 1] = 0;
+  P.drain();
+  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
+  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
 }
 
+void fa_set_legacy_chunk_bytes(size_t bytes) { g_chunk_bytes = bytes ? bytes : ((size_t)32 << 20); }
 void launch_flashattention_forward(float* Q, float* K, float* V, float* O, float* l, float* m, int B, int nh, int N,
                                    int d) {
   legacy_forward(Q, K, V, O, l, m, nullptr, 0, B, nh, N, d);

@@ -1,0 +1,84 @@
+"""The legacy host-pointer entry points (reference ABI, src/flashattention_kernel.cu:259,352,694,761) stream
+the (batch, head) units through an H2D / kernels / D2H pipeline in chunks.  Chunking must not change a
+single bit of the results (units are independent problems; the kernels are deterministic per unit in fp32
+mode, and in bf16 mode for O, dK, dV), and padding masks / kv_len must follow the chunk's batch index."""
+import numpy as np
+import pytest
+
+import flashattn_b200 as fb
+from oracle import attention_ref as R
+from tests.gpu_util import maxabs
+
+pytestmark = pytest.mark.gpu
+ops = fb.CudaKernelOps
+T = fb.tensor_from_numpy
+
+
+def _run(Q, K, V, dO, causal, key_mask):
+    fw = ops.flash_attention_causal_fw if causal else ops.flash_attention_fw
+    bw = ops.flash_attention_causal_bw if causal else ops.flash_attention_bw
+    km = T(key_mask) if key_mask is not None else None
+    q, k, v = T(Q), T(K), T(V)
+    O, m, l = fw(q, k, v, key_mask=km)
+    dQ, dK, dV = bw(q, k, v, O, T(dO), m, l, key_mask=km)
+    return [t.to_numpy().copy() for t in (O, m, l, dQ, dK, dV)]
+
+
+@pytest.fixture
+def lib():
+    lib = fb._lib.load("flashattention_kernel")
+    yield lib
+    lib.fa_set_legacy_chunk_bytes(0)
+    ops.set_flash_mode("fp32")
+
+
+@pytest.mark.parametrize("mode,d", [("fp32", 32), ("bf16", 128), ("bf16", 64)])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("masked", ["none", "padding", "generic"])
+def test_chunked_equals_single_chunk_and_oracle(lib, mode, d, causal, masked):
+    B, H, N = 3, 5, 200
+    rng = np.random.default_rng(31)
+    Q, K, V, dO = (R.round_bf16(rng.standard_normal((B, H, N, d)).astype(np.float32)) for _ in range(4))
+    key_mask = None
+    if masked == "padding":      # recognised as kv_len[] by the library (0 ... 0, -1e8 ...)
+        kv = np.array([200, 77, 130])
+        key_mask = np.where(np.arange(N)[None, :] < kv[:, None], 0.0, -1e8).astype(np.float32)
+    elif masked == "generic":    # arbitrary additive mask, different per batch
+        key_mask = np.where(rng.random((B, N)) < 0.3, -1e8, 0.0).astype(np.float32)
+        key_mask[:, 0] = 0.0
+    ops.set_flash_mode(mode)
+    lib.fa_set_legacy_chunk_bytes(1 << 40)           # one chunk per batch (a chunk never straddles batches)
+    whole = _run(Q, K, V, dO, causal, key_mask)
+    lib.fa_set_legacy_chunk_bytes(2 * N * d * 4)     # two heads per chunk -> 3 chunks per batch, ragged last
+    parts = _run(Q, K, V, dO, causal, key_mask)
+    lib.fa_set_legacy_chunk_bytes(1)                 # one head per chunk
+    single = _run(Q, K, V, dO, causal, key_mask)
+    names = ("O", "m", "l", "dQ", "dK", "dV")
+    for name, a, b, c in zip(names, whole, parts, single):
+        if mode == "bf16" and name == "dQ":          # dQ is an fp32 add-reduction across CTAs: rounding-level only
+            assert maxabs(a, b) <= 2.0 ** -7 * max(1.0, float(np.abs(a).max())), name
+            assert maxabs(a, c) <= 2.0 ** -7 * max(1.0, float(np.abs(a).max())), name
+        else:
+            np.testing.assert_array_equal(a, b, err_msg=name)
+            np.testing.assert_array_equal(a, c, err_msg=name)
+    tol = 1e-5 if mode == "fp32" else 2e-2
+    Oe, _, _ = R.attention_fwd(Q, K, V, causal=causal, key_mask=key_mask)
+    ge = R.attention_bwd(Q, K, V, dO, causal=causal, key_mask=key_mask)
+    assert maxabs(parts[0], Oe) < tol
+    for got, want in zip(parts[3:], ge):
+        assert maxabs(got, want) < tol * max(1.0, float(np.abs(want).max()))
+
+
+def test_many_chunks_cap(lib):
+    """More (batch, head) units than pipeline slots (256): heads are regrouped, nothing is dropped."""
+    B, H, N, d = 2, 300, 16, 8
+    rng = np.random.default_rng(5)
+    Q, K, V, dO = (rng.standard_normal((B, H, N, d)).astype(np.float32) for _ in range(4))
+    ops.set_flash_mode("fp32")
+    lib.fa_set_legacy_chunk_bytes(1)
+    got = _run(Q, K, V, dO, True, None)
+    Oe, _, _ = R.attention_fwd(Q, K, V, causal=True)
+    ge = R.attention_bwd(Q, K, V, dO, causal=True)
+    assert maxabs(got[0], Oe) < 1e-5
+    for g, w in zip(got[3:], ge):
+        assert maxabs(g, w) < 1e-5 * max(1.0, float(np.abs(w).max()))
