@@ -65,7 +65,7 @@ void fa_set_mode(int mode);
 int fa_get_mode(void);
 /* The legacy entry points are transfer-bound, so they cut the (batch, head) units into chunks of about
  * this many bytes of fp32 per tensor and overlap H2D of chunk c+1, the kernels of chunk c and D2H of
- * chunk c-1 on three streams (results are independent of the chunking).  Default 32 MiB, or env
+ * chunk c-1 on three streams (results are independent of the chunking).  Default 16 MiB (measured best of 4..64 on cfg4), or env
  * MINITORCH_FA_CHUNK_MB; 0 restores the default. */
 void fa_set_legacy_chunk_bytes(size_t bytes);
 

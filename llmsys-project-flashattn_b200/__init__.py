@@ -5,13 +5,17 @@ Layout:
   compile_cuda.sh      builds minitorch/cuda_kernels/{flashattention,softmax,layernorm}_kernel.so for sm_100a
   cuda_kernel_ops.py   CudaKernelOps: the reference's fused-op entry points over ctypes
   tensor.py            stand-alone host tensor + FlashAttention / Attn_Softmax / LayerNorm autograd nodes
+  modules_transformer.py  MultiHeadAttention / Linear / Dropout: the reference's call site of the path
   device.py            device-resident buffers + the *_dev entry points (bench / sharded runs)
 """
 from . import _lib, device, sharding
 from ._lib import FlashAttnError
 from .cuda_kernel_ops import CudaKernelOps
 from .tensor import (Attn_Softmax, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
-                     default_backend, tensor_from_numpy)
+                     default_backend, softmax, tensor_from_numpy)
+from . import modules_transformer
+from .modules_transformer import Dropout, Linear, MultiHeadAttention
 
 __all__ = ["CudaKernelOps", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
-           "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding"]
+           "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding", "softmax", "modules_transformer",
+           "MultiHeadAttention", "Linear", "Dropout"]

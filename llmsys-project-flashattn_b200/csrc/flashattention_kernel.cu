@@ -516,12 +516,12 @@ struct Chunk {
   int b, h0, hc;
 };
 // Heads per chunk: about kChunkBytes of fp32 per tensor, at most 256 chunks, whole heads only.
-static size_t g_chunk_bytes = 0;  // 0 = unresolved: env MINITORCH_FA_CHUNK_MB or 32 MiB
+static size_t g_chunk_bytes = 0;  // 0 = unresolved: env MINITORCH_FA_CHUNK_MB or 16 MiB
 static int plan_chunks(int B, int nh, int N, int d, Chunk* out, int cap) {
   if (!g_chunk_bytes) {
     const char* e = getenv("MINITORCH_FA_CHUNK_MB");
-    const long mb = e ? atol(e) : 32;
-    g_chunk_bytes = (size_t)(mb > 0 ? mb : 32) << 20;
+    const long mb = e ? atol(e) : 16;
+    g_chunk_bytes = (size_t)(mb > 0 ? mb : 16) << 20;
   }
   const size_t chunk_bytes = g_chunk_bytes;
   const size_t head_bytes = (size_t)N * d * 4;
@@ -713,7 +713,7 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
   else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
 }
 
-void fa_set_legacy_chunk_bytes(size_t bytes) { g_chunk_bytes = bytes ? bytes : ((size_t)32 << 20); }
+void fa_set_legacy_chunk_bytes(size_t bytes) { g_chunk_bytes = bytes ? bytes : ((size_t)16 << 20); }
 void launch_flashattention_forward(float* Q, float* K, float* V, float* O, float* l, float* m, int B, int nh, int N,
                                    int d) {
   legacy_forward(Q, K, V, O, l, m, nullptr, 0, B, nh, N, d);

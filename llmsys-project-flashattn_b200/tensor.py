@@ -91,8 +91,8 @@ class Function:
     @classmethod
     def apply(cls, *inputs: "HostTensor") -> "HostTensor":
         ctx = Context()
-        out = cls.forward(ctx, *[t.detach() for t in inputs])
-        if any(t.requires_grad() for t in inputs):
+        out = cls.forward(ctx, *[t.detach() if isinstance(t, HostTensor) else t for t in inputs])
+        if any(isinstance(t, HostTensor) and t.requires_grad() for t in inputs):
             out._node = (cls, ctx, inputs)
         return out
 
@@ -173,8 +173,39 @@ class HostTensor:
     def flash_attention_causal(self, k: "HostTensor", v: "HostTensor") -> "HostTensor":
         return FlashAttentionCausal.apply(self, k, v)
 
+    # ---- arithmetic the MultiHeadAttention call site needs (minitorch/tensor.py:196-260), all through
+    # combine.so's map / zip / reduce / MatrixMultiply ------------------------------------------------
+    def _lift(self, b) -> "HostTensor":
+        return b if isinstance(b, HostTensor) else tensor_from_numpy(np.array([b], dtype=datatype), backend=self.backend)
+
+    def __matmul__(self, b: "HostTensor") -> "HostTensor":
+        return MatMul.apply(self, b)
+
+    def __add__(self, b) -> "HostTensor":
+        return Add.apply(self, self._lift(b))
+
+    def __mul__(self, b) -> "HostTensor":
+        return Mul.apply(self, self._lift(b))
+
+    def __truediv__(self, b) -> "HostTensor":
+        return Mul.apply(self, Inv.apply(self._lift(b)))
+
+    def __neg__(self) -> "HostTensor":
+        return Neg.apply(self)
+
+    def __sub__(self, b) -> "HostTensor":
+        return Add.apply(self, Neg.apply(self._lift(b)))
+
+    def exp(self) -> "HostTensor":
+        return Exp.apply(self)
+
+    def sum(self, dim: Optional[int] = None) -> "HostTensor":
+        if dim is None:
+            return Sum.apply(self.contiguous().view(self.size), 0)
+        return Sum.apply(self, dim)
+
     # ---- autodiff -----------------------------------------------------------------
-    def backward(self, grad_output: "HostTensor") -> None:
+    def backward(self, grad_output: Optional["HostTensor"] = None) -> None:
         """Reverse-mode sweep over the recorded nodes (minitorch/autodiff.py:130-163)."""
         order, seen = [], set()
 
@@ -184,10 +215,14 @@ class HostTensor:
             seen.add(id(t))
             if t._node is not None:
                 for inp in t._node[2]:
-                    visit(inp)
+                    if isinstance(inp, HostTensor):
+                        visit(inp)
             order.append(t)
 
         visit(self)
+        if grad_output is None:
+            assert self.size == 1, "backward() without a gradient needs a scalar (minitorch/tensor.py:394-407)"
+            grad_output = tensor_from_numpy(np.ones(self.shape, dtype=datatype), backend=self.backend)
         grads = {id(self): grad_output}
         for t in reversed(order):
             g = grads.pop(id(t), None)
@@ -198,6 +233,7 @@ class HostTensor:
                     t.grad = g if t.grad is None else _add(t.grad, g)
                 continue
             fn, ctx, inputs = t._node
+            inputs = tuple(i for i in inputs if isinstance(i, HostTensor))
             outs = fn.backward(ctx, g)
             if not isinstance(outs, tuple):
                 outs = (outs,)
@@ -230,6 +266,128 @@ class _View:
     @staticmethod
     def backward(orig_shape, g):
         return g.contiguous().view(*orig_shape)
+
+
+def _unbroadcast(g: HostTensor, shape) -> HostTensor:
+    """Sum a gradient back to the shape of a broadcast operand (minitorch/tensor.py expand :293-326)."""
+    shape = tuple(shape)
+    if g.shape == shape:
+        return g
+    pad = len(g.shape) - len(shape)
+    for dim, n in enumerate(g.shape):
+        if dim < pad or shape[dim - pad] == 1 and n != 1:
+            g = g.f.add_reduce(g, dim)
+    return g.contiguous().view(*shape)
+
+
+class MatMul(Function):
+    """minitorch/tensor_functions.py:413-432."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return a.f.matrix_multiply(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_values
+
+        def tr(t):
+            order = list(range(len(t.shape)))
+            order[-2], order[-1] = order[-1], order[-2]
+            return t.permute(*order)
+
+        return (_unbroadcast(g.f.matrix_multiply(g, tr(b)), a.shape), _unbroadcast(g.f.matrix_multiply(tr(a), g), b.shape))
+
+
+class Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a.shape, b.shape)
+        return a.f.add_zip(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        sa, sb = ctx.saved_values
+        return _unbroadcast(g, sa), _unbroadcast(g, sb)
+
+
+class Mul(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return a.f.mul_zip(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_values
+        return _unbroadcast(g.f.mul_zip(g, b), a.shape), _unbroadcast(g.f.mul_zip(g, a), b.shape)
+
+
+class Neg(Function):
+    @staticmethod
+    def forward(ctx, a):
+        return a.f.neg_map(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.f.neg_map(g)
+
+
+class Inv(Function):
+    @staticmethod
+    def forward(ctx, a):
+        ctx.save_for_backward(a)
+        return a.f.inv_map(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_values
+        return g.f.inv_back_zip(a, g)
+
+
+class Exp(Function):
+    @staticmethod
+    def forward(ctx, a):
+        out = a.f.exp_map(a)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_values
+        return g.f.mul_zip(g, out)
+
+
+class Sum(Function):
+    @staticmethod
+    def forward(ctx, a, dim):
+        ctx.save_for_backward(a.shape)
+        return a.f.add_reduce(a, int(dim))
+
+    @staticmethod
+    def backward(ctx, g):
+        (shape,) = ctx.saved_values
+        return g.f.add_zip(g, g.zeros(shape))   # broadcast the reduced gradient back over `dim`
+
+
+class Max(Function):
+    """Row max used by the composed softmax (minitorch/nn.py:63-101); no gradient flows through it in
+    softmax(x) = exp(x - max) / sum: the two contributions cancel exactly, as in the reference's usage."""
+
+    @staticmethod
+    def forward(ctx, a, dim):
+        return a.f.max_reduce(a, int(dim))
+
+    @staticmethod
+    def backward(ctx, g):
+        return None
+
+
+def softmax(x: HostTensor, dim: int) -> HostTensor:
+    """Composed softmax, op for op as minitorch/nn.py:104-123 (max-subtracted, no epsilon)."""
+    e = (x - Max.apply(x.detach(), dim)).exp()
+    return e / e.sum(dim)
 
 
 class Attn_Softmax(Function):
