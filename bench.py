@@ -337,6 +337,20 @@ def main():
 
 def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
     """Same step through launch_flashattention_{forward,backward}_masked (host fp32 buffers, pinned)."""
+    # 8 pinned fp32 tensors per rank (4.3 GB at cfg4): with several ranks on one host, keep the total pinned
+    # footprint under ~40 % of the available host memory by shrinking this rank's e2e batch if necessary.
+    from flashattn_b200 import device as dev
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    try:
+        avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+        per_b = 8 * H * N * d * 4 + 2 * H * N * 4
+        B = max(1, min(B, int(0.4 * avail / world / per_b)))
+    except Exception:
+        pass
+    if kv_len is not None:
+        kv_len = kv_len[:B]
+    flops_step = dev.attn_flops(B, H, N, d, causal, kv_len, backward=False) + \
+        dev.attn_flops(B, H, N, d, causal, kv_len, backward=True)
     n = B * H * N * d
     r = B * H * N
 
@@ -389,7 +403,7 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
     h2d = (3 * n + 5 * n + 2 * r) * 4
     d2h = (n + 2 * r + 3 * n) * 4
     return {"value": total / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "steps": steps, "ms_per_step": dt / steps * 1e3, "batch_per_gpu": B,
             "path": "launch_flashattention_forward_masked + launch_flashattention_backward_masked (legacy C ABI, "
                     "fp32 pinned host buffers, FA_MODE_BF16), wall clock incl. H2D/D2H"}
 
