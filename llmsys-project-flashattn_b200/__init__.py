@@ -12,10 +12,13 @@ from . import _lib, device, sharding
 from ._lib import FlashAttnError
 from .cuda_kernel_ops import CudaKernelOps
 from .tensor import (Attn_Softmax, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
-                     default_backend, softmax, tensor_from_numpy)
+                     default_backend, logsumexp, one_hot, softmax, softmax_loss, GELU,
+                     tensor_from_numpy)
 from . import modules_transformer
-from .modules_transformer import Dropout, Linear, MultiHeadAttention
+from .modules_transformer import (DecoderLM, Dropout, Embedding, FeedForward, FusedLayerNorm, LayerNorm1d, Linear,
+                                  MultiHeadAttention, TransformerLayer)
 
 __all__ = ["CudaKernelOps", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
            "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding", "softmax", "modules_transformer",
-           "MultiHeadAttention", "Linear", "Dropout"]
+           "MultiHeadAttention", "Linear", "Dropout", "DecoderLM", "TransformerLayer", "FeedForward", "Embedding",
+           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU"]

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .tensor import HostTensor, TensorBackend, default_backend, softmax, tensor_from_numpy
+from .tensor import GELU, HostTensor, TensorBackend, default_backend, one_hot, softmax, tensor_from_numpy
 
 datatype = np.float32
 
@@ -29,14 +29,18 @@ class Module:
     def __init__(self):
         self.training = True
 
-    def parameters(self):
+    def named_parameters(self):
+        """(dotted name, Parameter) pairs, named like minitorch/module.py:48-67."""
         out = []
-        for v in self.__dict__.values():
+        for k, v in self.__dict__.items():
             if isinstance(v, Parameter):
-                out.append(v)
+                out.append((k, v))
             elif isinstance(v, Module):
-                out.extend(v.parameters())
+                out.extend((f"{k}.{n}", p) for n, p in v.named_parameters())
         return out
+
+    def parameters(self):
+        return [p for _, p in self.named_parameters()]
 
     def train(self):
         self.training = True
@@ -149,3 +153,127 @@ class MultiHeadAttention(Module):
         else:
             attn = self.self_attention(q, kT, v)
         return self.out_projection(attn.view(batch_size * seq_len, n_embd)).view(batch_size, seq_len, n_embd)
+
+
+class Embedding(Module):
+    """One-hot @ weights, exactly the reference's formulation (minitorch/modules_basic.py:29-71)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, backend: TensorBackend = None):
+        super().__init__()
+        self.backend = backend
+        self.num_embeddings = num_embeddings
+        self.embedding_dim = embedding_dim
+        self.weights = Parameter(tensor_from_numpy(np.random.normal(0, 1, (num_embeddings, embedding_dim)),
+                                                   backend=backend, requires_grad=True))
+
+    def forward(self, x: HostTensor) -> HostTensor:
+        bs, seq_len = x.shape
+        hot = one_hot(x, self.num_embeddings).view(bs * seq_len, self.num_embeddings)
+        return (hot @ self.weights.value).view(bs, seq_len, self.embedding_dim)
+
+
+class LayerNorm1d(Module):
+    """Composed layer norm.  Like the reference (minitorch/modules_basic.py:158-199) the forward returns the
+    normalised input WITHOUT applying weights / bias (they exist as parameters and receive no gradient)."""
+
+    def __init__(self, dim: int, eps: float, backend: TensorBackend = None):
+        super().__init__()
+        self.dim = dim
+        self.eps = eps
+        self.weights = Parameter(tensor_from_numpy(np.ones((dim,)), backend=backend))
+        self.bias = Parameter(tensor_from_numpy(np.zeros((dim,)), backend=backend))
+
+    def forward(self, x: HostTensor) -> HostTensor:
+        mean = x.mean(dim=1)
+        var = x.var(dim=1)
+        return (x - mean) / (var + self.eps) ** 0.5
+
+
+class FusedLayerNorm(Module):
+    """x.layernorm(gamma, beta) through layernorm_kernel.so (minitorch/modules_basic.py:202-210)."""
+
+    def __init__(self, n_embd: int, backend: TensorBackend = None):
+        super().__init__()
+        self.n_embd = n_embd
+        self.gamma = tensor_from_numpy(np.ones((n_embd,)), backend=backend)
+        self.beta = tensor_from_numpy(np.zeros((n_embd,)), backend=backend)
+
+    def forward(self, x: HostTensor) -> HostTensor:
+        return x.layernorm(self.gamma, self.beta)
+
+
+class FeedForward(Module):
+    """Linear -> GELU -> Linear -> dropout (minitorch/modules_transfomer.py:232-275)."""
+
+    def __init__(self, n_embd: int, middle_dim: int = 256, p_dropout: float = 0.1, bias: bool = True,
+                 backend: TensorBackend = None):
+        super().__init__()
+        self.linear_in = Linear(n_embd, middle_dim, bias=bias, backend=backend)
+        self.linear_out = Linear(middle_dim, n_embd, bias=bias, backend=backend)
+        self.dropout = Dropout(p_dropout)
+
+    def forward(self, x: HostTensor) -> HostTensor:
+        batch_size, seq_len, n_embd = x.shape
+        x = GELU(self.linear_in(x.contiguous().view(batch_size * seq_len, n_embd)))
+        return self.dropout(self.linear_out(x)).view(batch_size, seq_len, n_embd)
+
+
+class TransformerLayer(Module):
+    """Pre-LN block (minitorch/modules_transfomer.py:278-336).  The flags reach MultiHeadAttention by KEYWORD:
+    the reference's positional call hands `use_flash_attention` to `use_fused_kernel`."""
+
+    def __init__(self, n_embd: int, n_head: int, p_dropout: float = 0.1, ln_eps: float = 1e-8, bias: bool = True,
+                 backend: TensorBackend = None, use_fused_kernel: bool = False, use_flash_attention: bool = False):
+        super().__init__()
+        self.attention = MultiHeadAttention(n_embd, n_head, causal=True, p_dropout=p_dropout, bias=bias,
+                                            backend=backend, use_fused_kernel=use_fused_kernel,
+                                            use_flash_attention=use_flash_attention)
+        self.ff = FeedForward(n_embd, 256, p_dropout, bias, backend)
+        self.use_fused_kernel = use_fused_kernel
+        if not use_fused_kernel:
+            self.ln_1 = LayerNorm1d(n_embd, ln_eps, backend)
+            self.ln_2 = LayerNorm1d(n_embd, ln_eps, backend)
+        else:
+            self.ln_1 = FusedLayerNorm(n_embd, backend)
+            self.ln_2 = FusedLayerNorm(n_embd, backend)
+
+    def forward(self, x: HostTensor) -> HostTensor:
+        batch_size, seq_len, x_dim = x.shape
+        a = self.ln_1(x.contiguous().view(batch_size * seq_len, x_dim)).view(batch_size, seq_len, x_dim)
+        a = self.attention(a) + x
+        y = self.ln_2(a.contiguous().view(batch_size * seq_len, x_dim)).view(batch_size, seq_len, x_dim)
+        return self.ff(y) + a
+
+
+class DecoderLM(Module):
+    """Decoder-only Pre-LN transformer with four layers (minitorch/modules_transfomer.py:339-453); config #2 of
+    BASELINE.json is DecoderLM(n_vocab=10000, n_embd=256, n_head=8, n_positions=40) with flash attention."""
+
+    def __init__(self, n_vocab: int, n_embd: int, n_head: int, n_positions: int, p_dropout: float = 0.1,
+                 ln_eps: float = 1e-5, bias: bool = True, backend: TensorBackend = None,
+                 use_fused_kernel: bool = False, use_flash_attention: bool = False):
+        super().__init__()
+        self.backend = backend if backend is not None else default_backend()
+        self.n_embd = n_embd
+        self.n_vocab = n_vocab
+        self.token_embeddings = Embedding(n_vocab, n_embd, self.backend)
+        self.position_embeddings = Embedding(n_vocab, n_embd, self.backend)   # (sic) sized by n_vocab in the reference
+        kw = dict(p_dropout=p_dropout, ln_eps=ln_eps, bias=bias, backend=self.backend,
+                  use_fused_kernel=use_fused_kernel, use_flash_attention=use_flash_attention)
+        self.t_layer_1 = TransformerLayer(n_embd, n_head, **kw)
+        self.t_layer_2 = TransformerLayer(n_embd, n_head, **kw)
+        self.t_layer_3 = TransformerLayer(n_embd, n_head, **kw)
+        self.t_layer_4 = TransformerLayer(n_embd, n_head, **kw)
+        self.dropout = Dropout(p_dropout)
+        self.lm_head = Linear(n_embd, n_vocab, bias, self.backend)
+        self.use_fused_kernel = use_fused_kernel
+        self.ln = FusedLayerNorm(n_embd, self.backend) if use_fused_kernel else LayerNorm1d(n_embd, ln_eps, self.backend)
+
+    def forward(self, idx: HostTensor) -> HostTensor:
+        batch_size, seq_len = idx.shape
+        position_id = tensor_from_numpy(np.arange(seq_len, dtype=datatype).reshape(1, seq_len), backend=self.backend)
+        x = self.token_embeddings(idx) + self.position_embeddings(position_id).view(1, seq_len, self.n_embd)
+        for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
+            x = layer(x)
+        x = self.ln(x.contiguous().view(batch_size * seq_len, self.n_embd))
+        return self.lm_head(x).view(batch_size, seq_len, self.n_vocab)

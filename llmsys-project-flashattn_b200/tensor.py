@@ -196,8 +196,31 @@ class HostTensor:
     def __sub__(self, b) -> "HostTensor":
         return Add.apply(self, Neg.apply(self._lift(b)))
 
+    def __radd__(self, b) -> "HostTensor":
+        return self + b
+
+    def __rmul__(self, b) -> "HostTensor":
+        return self * b
+
+    def __pow__(self, b) -> "HostTensor":
+        return PowerScalar.apply(self, self._lift(b))
+
     def exp(self) -> "HostTensor":
         return Exp.apply(self)
+
+    def log(self) -> "HostTensor":
+        return Log.apply(self)
+
+    def tanh(self) -> "HostTensor":
+        return Tanh.apply(self)
+
+    def mean(self, dim: Optional[int] = None) -> "HostTensor":
+        return self.sum(dim) / (self.shape[dim] if dim is not None else self.size)
+
+    def var(self, dim: int) -> "HostTensor":
+        """Biased variance, keeps the reduced dim (minitorch/tensor.py:248-260)."""
+        diff = (self - self.sum(dim) / self.shape[dim]) ** 2
+        return diff.sum(dim) / self.shape[dim]
 
     def sum(self, dim: Optional[int] = None) -> "HostTensor":
         if dim is None:
@@ -372,22 +395,87 @@ class Sum(Function):
 
 
 class Max(Function):
-    """Row max used by the composed softmax (minitorch/nn.py:63-101); no gradient flows through it in
-    softmax(x) = exp(x - max) / sum: the two contributions cancel exactly, as in the reference's usage."""
+    """Row max with the reference's argmax gradient (minitorch/nn.py:81-97)."""
 
     @staticmethod
     def forward(ctx, a, dim):
-        return a.f.max_reduce(a, int(dim))
+        out = a.f.max_reduce(a, int(dim))
+        ctx.save_for_backward(a, out)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        return None
+        a, out = ctx.saved_values
+        return g.f.mul_zip(g.f.eq_zip(out, a), g)
+
+
+class PowerScalar(Function):
+    """a ** scalar (minitorch/tensor_functions.py:133-183)."""
+
+    @staticmethod
+    def forward(ctx, a, scalar):
+        ctx.save_for_backward(a, scalar)
+        return a.f.pow_scalar_zip(a, scalar)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, scalar = ctx.saved_values
+        f = g.f
+        return f.mul_zip(g, f.mul_zip(scalar, f.pow_scalar_zip(a, f.add_zip(scalar, scalar._lift(-1.0))))), None
+
+
+class Tanh(Function):
+    @staticmethod
+    def forward(ctx, a):
+        out = a.f.tanh_map(a)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_values
+        f = g.f
+        return f.mul_zip(g, f.add_zip(f.neg_map(f.mul_zip(out, out)), out._lift(1.0)))
+
+
+class Log(Function):
+    @staticmethod
+    def forward(ctx, a):
+        ctx.save_for_backward(a)
+        return a.f.log_map(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_values
+        return g.f.log_back_zip(a, g)
 
 
 def softmax(x: HostTensor, dim: int) -> HostTensor:
     """Composed softmax, op for op as minitorch/nn.py:104-123 (max-subtracted, no epsilon)."""
-    e = (x - Max.apply(x.detach(), dim)).exp()
+    e = (x - Max.apply(x, dim)).exp()
     return e / e.sum(dim)
+
+
+def logsumexp(x: HostTensor, dim: int) -> HostTensor:
+    """minitorch/nn.py:229-246 (keeps the reduced dim)."""
+    mx = Max.apply(x, dim)
+    return mx + (x - mx).exp().sum(dim).log()
+
+
+def one_hot(x: HostTensor, num_classes: int) -> HostTensor:
+    """minitorch/nn.py:212-222: a host-side index-to-row expansion (np.eye lookup), no arithmetic."""
+    return tensor_from_numpy(np.eye(num_classes, dtype=datatype)[x.to_numpy().astype(int)], backend=x.backend)
+
+
+def softmax_loss(logits: HostTensor, target: HostTensor) -> HostTensor:
+    """Cross entropy with reduction=None (minitorch/nn.py:251-271): (minibatch, C), (minibatch,) -> (minibatch,)."""
+    result = logsumexp(logits, dim=1) - (logits * one_hot(target, logits.shape[1])).sum(dim=1)
+    return result.view(logits.shape[0])
+
+
+def GELU(x: HostTensor) -> HostTensor:
+    """tanh-approximated GELU, op for op as minitorch/nn.py:205-209."""
+    return 0.5 * x * (1 + (float(np.sqrt(2 / np.pi)) * (x + 0.044715 * (x ** 3))).tanh())
 
 
 class Attn_Softmax(Function):

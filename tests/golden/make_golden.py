@@ -256,12 +256,50 @@ def gen_combine():
     print("combine", len(out), "arrays")
 
 
+def gen_decoder():
+    """Config #2's model family at fixture size: the reference's DecoderLM (minitorch/modules_transfomer.py:339-453)
+    on its composed CPU path, with the MLE loss of project/run_machine_translation.py:164-192.  Flags are passed by
+    KEYWORD (the reference's positional calls mis-route use_flash_attention).  Saves every parameter
+    by its named_parameters() name, the logits, the loss and a few gradients."""
+    np.random.seed(7)
+    n_vocab, n_embd, n_head, n_pos, B = 97, 64, 8, 40, 3
+    model = minitorch.DecoderLM(n_vocab=n_vocab, n_embd=n_embd, n_head=n_head, n_positions=n_pos, p_dropout=0.0,
+                                ln_eps=1e-5, bias=True, backend=backend)
+    rng = np.random.default_rng(11111)
+    ids = rng.integers(0, n_vocab, (B, n_pos))
+    weights = np.zeros((B, n_pos), dtype=datatype)
+    weights[:, n_pos // 2:] = 1.0
+    input_ids, labels, lw = ids[:, :-1], ids[:, 1:], weights[:, 1:]
+    idx = mt(input_ids, grad=False)
+    logits = model(idx=idx)
+    bs, l, c = logits.shape
+    loss = minitorch.nn.softmax_loss(logits=logits.view(bs * l, c), target=mt(labels, grad=False).view(bs * l))
+    w = mt(lw, grad=False).view(bs * l)
+    total = (loss * w).sum() / w.sum()
+    total.backward()
+    out = dict(input_ids=input_ids.astype(np.int64), labels=labels.astype(np.int64), label_token_weights=lw,
+               logits=logits.to_numpy(), loss=np.array(total.to_numpy()).reshape(-1)[:1],
+               cfg=np.array([n_vocab, n_embd, n_head, n_pos]))
+    for name, prm in model.named_parameters():
+        out["p:" + name] = prm.value.to_numpy()
+        if prm.value.grad is not None and (name.endswith("q_projection.weights") or name.startswith("lm_head")
+                                           or name.startswith("token_embeddings") or name.endswith("linear_in.bias")
+                                           or name.endswith("out_projection.bias")):
+            out["g:" + name] = prm.value.grad.to_numpy()
+    np.savez_compressed(os.path.join(HERE, "decoder_small.npz"), **out)
+    print("decoder logits", logits.shape, "loss", float(out["loss"][0]), "arrays", len(out))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "combine":
         gen_combine()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "decoder":
+        gen_decoder()
         sys.exit(0)
     gen_attention()
     gen_mha()
     gen_softmax()
     gen_layernorm()
     gen_combine()
+    gen_decoder()

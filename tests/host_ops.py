@@ -1,0 +1,82 @@
+"""``OracleOps``: a CPU stand-in for ``CudaKernelOps`` built on the oracle (TEST INFRASTRUCTURE).
+
+Same static-method surface (map / zip / reduce / matrix_multiply and the eight fused ops), numpy arithmetic
+from ``oracle/``.  It lets the ``-m "not gpu"`` suite drive the host-side logic -- HostTensor autograd, the
+MultiHeadAttention / TransformerLayer / DecoderLM call sites -- against the golden vectors without a GPU.
+The product never imports this module.
+"""
+import numpy as np
+
+from flashattn_b200.cuda_kernel_ops import _fn_id, shape_broadcast
+from oracle import attention_ref as R
+from oracle import combine_ref as C
+
+f32 = np.float32
+
+
+def _new(ref, arr):
+    arr = np.array(arr, dtype=f32, order="C")     # always a fresh writable buffer
+    return type(ref).make(arr.reshape(-1), tuple(arr.shape), backend=ref.backend)
+
+
+class OracleOps:
+    cuda = False
+
+    @staticmethod
+    def map(fn):
+        fid = _fn_id(fn)
+        return lambda a, out=None: _new(a, C.tensor_map(fid, a.to_numpy()))
+
+    @staticmethod
+    def zip(fn):
+        fid = _fn_id(fn)
+
+        def ret(a, b):
+            shape = shape_broadcast(a.shape, b.shape)
+            return _new(a, np.broadcast_to(C.tensor_zip(fid, a.to_numpy(), b.to_numpy()), shape))
+        return ret
+
+    @staticmethod
+    def reduce(fn, start=0.0):
+        fid = _fn_id(fn)
+        return lambda a, dim: _new(a, C.tensor_reduce(fid, a.to_numpy(), int(dim), start))
+
+    @staticmethod
+    def matrix_multiply(a, b):
+        return _new(a, C.matrix_multiply(a.to_numpy(), b.to_numpy()))
+
+    @staticmethod
+    def _fw(Q, K, V, causal):
+        O, m, l = R.attention_fwd(Q.to_numpy(), K.to_numpy(), V.to_numpy(), causal=causal)
+        return _new(Q, O), _new(Q, m), _new(Q, l)
+
+    @staticmethod
+    def _bw(Q, K, V, O, dO, m, l, causal):
+        g = R.attention_bwd(Q.to_numpy(), K.to_numpy(), V.to_numpy(), dO.to_numpy(), causal=causal)
+        return tuple(_new(Q, x) for x in g)
+
+    flash_attention_fw = staticmethod(lambda Q, K, V: OracleOps._fw(Q, K, V, False))
+    flash_attention_causal_fw = staticmethod(lambda Q, K, V: OracleOps._fw(Q, K, V, True))
+    flash_attention_bw = staticmethod(lambda Q, K, V, O, dO, m, l: OracleOps._bw(Q, K, V, O, dO, m, l, False))
+    flash_attention_causal_bw = staticmethod(lambda Q, K, V, O, dO, m, l: OracleOps._bw(Q, K, V, O, dO, m, l, True))
+
+    @staticmethod
+    def attn_softmax_fw(inp, mask, mask_future=False):
+        y = R.attn_softmax_fw(inp.to_numpy(), None if mask is None else mask.to_numpy(), mask_future)
+        inp._tensor._storage[:] = np.ascontiguousarray(y, dtype=f32).reshape(-1)   # in place, like the kernel
+        return inp
+
+    @staticmethod
+    def attn_softmax_bw(out_grad, soft_inp):
+        return _new(out_grad, R.attn_softmax_bw(out_grad.to_numpy(), soft_inp.to_numpy())), soft_inp
+
+    @staticmethod
+    def layernorm_fw(inp, gamma, beta):
+        y, var, mean = R.layernorm_fw(inp.to_numpy(), gamma.to_numpy(), beta.to_numpy())
+        return _new(inp, y), _new(inp, var), _new(inp, mean)
+
+    @staticmethod
+    def layernorm_bw(out_grad, inp, gamma, beta, var, mean):
+        dx, dg, db = R.layernorm_bw(out_grad.to_numpy(), inp.to_numpy(), gamma.to_numpy(), beta.to_numpy(),
+                                    var.to_numpy(), mean.to_numpy())
+        return _new(inp, dx), _new(inp, np.reshape(dg, (1, -1))), _new(inp, np.reshape(db, (1, -1)))

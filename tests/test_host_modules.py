@@ -1,0 +1,104 @@
+"""Host-side logic on CPU: HostTensor autograd and the MultiHeadAttention / DecoderLM call sites driven through
+``OracleOps`` (tests/host_ops.py -- the oracle behind the CudaKernelOps surface), checked against golden vectors
+made from the reference itself (tests/golden/make_golden.py).  The same modules run on the GPU libraries in
+tests/test_gpu_mha_module.py and tests/test_gpu_decoder.py."""
+import os
+
+import numpy as np
+import pytest
+
+import flashattn_b200 as fb
+from tests.gpu_util import golden
+from tests.host_ops import OracleOps
+
+BACKEND = fb.TensorBackend(OracleOps)
+
+
+def T(a, requires_grad=False):
+    return fb.tensor_from_numpy(np.asarray(a, dtype=np.float32), backend=BACKEND, requires_grad=requires_grad)
+
+
+def load_decoder(z, **flags):
+    n_vocab, n_embd, n_head, n_pos = (int(v) for v in z["cfg"])
+    backend = flags.pop("backend", BACKEND)
+    model = fb.DecoderLM(n_vocab=n_vocab, n_embd=n_embd, n_head=n_head, n_positions=n_pos, p_dropout=0.0,
+                         ln_eps=1e-5, bias=True, backend=backend, **flags)
+    params = dict(model.named_parameters())
+    names = [k[2:] for k in z.files if k.startswith("p:")]
+    if not flags.get("use_fused_kernel"):           # FusedLayerNorm holds plain tensors, not Parameters
+        assert sorted(params) == sorted(names)      # same parameter tree as the reference's named_parameters()
+    for name in (n for n in names if n in params):
+        params[name].value = fb.tensor_from_numpy(z["p:" + name], backend=backend, requires_grad=True)
+    return model, params
+
+
+def decoder_loss(model, z, backend=BACKEND):
+    mk = lambda a: fb.tensor_from_numpy(np.asarray(a, dtype=np.float32), backend=backend)
+    logits = model(mk(z["input_ids"]))
+    bs, l, c = logits.shape
+    loss = fb.softmax_loss(logits.view(bs * l, c), mk(z["labels"]).view(bs * l))
+    w = mk(z["label_token_weights"]).view(bs * l)
+    return logits, (loss * w).sum() / w.sum()
+
+
+@pytest.mark.parametrize("branch", ["composed", "flash", "fused"])
+def test_decoder_lm_matches_reference_golden(branch):
+    z = np.load(golden("decoder_small.npz")[0])
+    model, params = load_decoder(z, use_flash_attention=branch == "flash", use_fused_kernel=branch == "fused")
+    logits, total = decoder_loss(model, z)
+    # the fused branch swaps LayerNorm1d(eps=1e-5) for the fused kernel's fixed 1e-8 epsilon: same model up to that
+    tol = 1e-4 if branch == "fused" else 2e-5
+    np.testing.assert_allclose(logits.to_numpy(), z["logits"], atol=tol * 10, rtol=tol)
+    assert abs(float(total.to_numpy().reshape(-1)[0]) - float(z["loss"][0])) < tol
+    total.backward()
+    for k in z.files:
+        if k.startswith("g:"):
+            got = params[k[2:]].value.grad.to_numpy()
+            np.testing.assert_allclose(got, z[k], atol=tol * max(1.0, float(np.abs(z[k]).max())), rtol=10 * tol,
+                                       err_msg=k)
+
+
+@pytest.mark.parametrize("branch", ["flash", "fused", "composed"])
+@pytest.mark.parametrize("path", golden("mha_cfg1_*.npz"), ids=os.path.basename)
+def test_mha_module_host_logic(path, branch):
+    z = np.load(path)
+    layer = fb.MultiHeadAttention(z["X"].shape[-1], int(z["n_head"]), causal=bool(z["causal"]), p_dropout=0.0,
+                                  bias=False, backend=BACKEND, use_flash_attention=branch == "flash",
+                                  use_fused_kernel=branch == "fused")
+    for lin, key in ((layer.q_projection, "Wq"), (layer.k_projection, "Wk"), (layer.v_projection, "Wv"),
+                     (layer.out_projection, "Wo")):
+        lin.weights.value = T(z[key], requires_grad=True)
+    X = T(z["X"], requires_grad=True)
+    Y = layer(X)
+    np.testing.assert_allclose(Y.to_numpy(), z["Y_ref"], atol=1e-5, rtol=1e-5)
+    Y.sum().backward()
+    np.testing.assert_allclose(X.grad.to_numpy(), z["dX_ref"], atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(layer.q_projection.weights.value.grad.to_numpy(), z["dWq_ref"], atol=2e-4, rtol=1e-4)
+
+
+def test_autograd_nodes_against_finite_differences():
+    """GELU(x @ W + b).var / logsumexp / pow chain: analytic gradient vs central differences (fp64 oracle ops)."""
+    rng = np.random.default_rng(0)
+    x0 = rng.standard_normal((5, 7)).astype(np.float32)
+    W0 = rng.standard_normal((7, 3)).astype(np.float32)
+    b0 = rng.standard_normal((3,)).astype(np.float32)
+
+    def f(xv, Wv, bv):
+        x, W, b = T(xv, True), T(Wv, True), T(bv, True)
+        y = fb.GELU(x @ W + b)
+        out = (fb.logsumexp(y, dim=1).view(5) * 0.5).sum() + (y.var(dim=0) + 1.0) .log().sum() - (y ** 2).mean()
+        return out, (x, W, b)
+
+    out, leaves = f(x0, W0, b0)
+    out.backward()
+    for arr, leaf in zip((x0, W0, b0), leaves):
+        g = leaf.grad.to_numpy()
+        for idx in [tuple(rng.integers(0, s) for s in arr.shape) for _ in range(4)]:
+            e = 1e-2
+            hi, lo = arr.copy(), arr.copy()
+            hi[idx] += e
+            lo[idx] -= e
+            args_hi = [hi if a is arr else a for a in (x0, W0, b0)]
+            args_lo = [lo if a is arr else a for a in (x0, W0, b0)]
+            fd = (float(f(*args_hi)[0].to_numpy().reshape(-1)[0]) - float(f(*args_lo)[0].to_numpy().reshape(-1)[0])) / (2 * e)
+            assert abs(fd - g[idx]) < 5e-3 * max(1.0, abs(fd)), (idx, fd, g[idx])
