@@ -513,9 +513,11 @@ struct LegacyPipe {
 static LegacyPipe g_pipe;
 
 struct Chunk {
-  int b, h0, hc;
+  int b, nb, h0, hc;   // batches [b, b+nb) x heads [h0, h0+hc); nb > 1 only with all heads (contiguous slab)
 };
-// Heads per chunk: about kChunkBytes of fp32 per tensor, at most 256 chunks, whole heads only.
+// About g_chunk_bytes of fp32 per tensor and chunk, at most `cap` chunks: whole batches when a batch fits in a
+// chunk (small problems become ONE chunk: every extra chunk costs ~10 driver calls), otherwise groups of heads
+// inside one batch.
 static size_t g_chunk_bytes = 0;  // 0 = unresolved: env MINITORCH_FA_CHUNK_MB or 16 MiB
 static int plan_chunks(int B, int nh, int N, int d, Chunk* out, int cap) {
   if (!g_chunk_bytes) {
@@ -525,13 +527,21 @@ static int plan_chunks(int B, int nh, int N, int d, Chunk* out, int cap) {
   }
   const size_t chunk_bytes = g_chunk_bytes;
   const size_t head_bytes = (size_t)N * d * 4;
+  const size_t batch_bytes = head_bytes * nh;
   int hc = (int)(chunk_bytes / head_bytes);
   if (hc < 1) hc = 1;
   if (hc > nh) hc = nh;
-  while ((size_t)B * ((nh + hc - 1) / hc) > (size_t)cap) ++hc;
+  while (hc < nh && (size_t)B * ((nh + hc - 1) / hc) > (size_t)cap) ++hc;
   int n = 0;
+  if (hc == nh) {
+    size_t nb = batch_bytes <= chunk_bytes ? chunk_bytes / batch_bytes : 1;
+    if (nb < 1) nb = 1;
+    while (((size_t)B + nb - 1) / nb > (size_t)cap) ++nb;
+    for (int b = 0; b < B; b += (int)nb) out[n++] = Chunk{b, (B - b < (int)nb) ? B - b : (int)nb, 0, nh};
+    return n;
+  }
   for (int b = 0; b < B; ++b)
-    for (int h0 = 0; h0 < nh; h0 += hc) out[n++] = Chunk{b, h0, (nh - h0 < hc) ? nh - h0 : hc};
+    for (int h0 = 0; h0 < nh; h0 += hc) out[n++] = Chunk{b, 1, h0, (nh - h0 < hc) ? nh - h0 : hc};
   return n;
 }
 
@@ -580,15 +590,15 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
   int rc = FA_OK;
   for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
     const Chunk& ck = chunks[c];
-    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.hc * N * d;
-    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.hc * N;
+    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
+    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
     step(cudaMemcpyAsync(dQ_ + off, Q + off, cn * 4, cudaMemcpyHostToDevice, P.in));
     step(cudaMemcpyAsync(dK_ + off, K + off, cn * 4, cudaMemcpyHostToDevice, P.in));
     step(cudaMemcpyAsync(dV_ + off, V + off, cn * 4, cudaMemcpyHostToDevice, P.in));
     step(cudaEventRecord(P.ev_in[c], P.in));
     step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
     fa_attn_desc ca = a;
-    ca.B = 1, ca.H = ck.hc;
+    ca.B = ck.nb, ca.H = ck.hc;
     if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
     if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
     fa_stream_t cs = reinterpret_cast<fa_stream_t>(P.comp);
@@ -674,8 +684,8 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
   int rc = FA_OK;
   for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
     const Chunk& ck = chunks[c];
-    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.hc * N * d;
-    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.hc * N;
+    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
+    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
     for (int i = 0; i < 5; ++i)
       step(cudaMemcpyAsync(buf[i] + off, host_in[i] + off, cn * 4, cudaMemcpyHostToDevice, P.in));
     step(cudaMemcpyAsync(dm + roff, m + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
@@ -683,7 +693,7 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
     step(cudaEventRecord(P.ev_in[c], P.in));
     step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
     fa_attn_desc ca = a;
-    ca.B = 1, ca.H = ck.hc;
+    ca.B = ck.nb, ca.H = ck.hc;
     if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
     if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
     fa_stream_t cs = reinterpret_cast<fa_stream_t>(P.comp);
