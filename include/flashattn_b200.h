@@ -38,6 +38,9 @@ int fa_device_count(void);
 int fa_set_device(int dev);
 void* fa_malloc(size_t bytes);                 /* NULL on failure */
 void* fa_malloc_host(size_t bytes);            /* pinned host memory */
+void* fa_malloc_async(size_t bytes, fa_stream_t stream);   /* stream-ordered, from the cached default pool */
+int fa_free_async(void* dptr, fa_stream_t stream);
+int fa_memset_async(void* dptr, int byte, size_t bytes, fa_stream_t stream);
 int fa_free(void* dptr);
 int fa_free_host(void* hptr);
 int fa_memset(void* dptr, int byte, size_t bytes);
@@ -173,6 +176,18 @@ void tensorReduce(float* out, int* out_shape, int* out_strides, int out_size, fl
                   int* a_strides, int reduce_dim, double reduce_value, int shape_size, int fn_id);
 void MatrixMultiply(float* out, int* out_shape, int* out_strides, float* a_storage, int* a_shape, int* a_strides,
                     float* b_storage, int* b_shape, int* b_strides, int batch, int m, int p);
+/* Device-pointer variants (additive): the same kernels on operands already resident in HBM, asynchronous on
+ * `stream`; shape / stride arrays stay host int32.  Operands of lower rank broadcast right-aligned, as in
+ * tensorZip.  fa_matmul_dev: 3-D (batch | 1, m, n) @ (batch | 1, n, p) -> (batch, m, p), arbitrary strides. */
+int fa_map_dev(float* out, const int* out_shape, const int* out_strides, int out_nd, const float* in,
+               const int* in_shape, const int* in_strides, int in_nd, int fn_id, fa_stream_t stream);
+int fa_zip_dev(float* out, const int* out_shape, const int* out_strides, int out_nd, const float* a,
+               const int* a_shape, const int* a_strides, int a_nd, const float* b, const int* b_shape,
+               const int* b_strides, int b_nd, int fn_id, fa_stream_t stream);
+int fa_reduce_dev(float* out, const int* out_shape, const int* out_strides, const float* a, const int* a_shape,
+                  const int* a_strides, int nd, int reduce_dim, double reduce_value, int fn_id, fa_stream_t stream);
+int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, const float* a, const int* a_shape,
+                  const int* a_strides, const float* b, const int* b_shape, const int* b_strides, fa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,9 @@ _COMMON = {
     "fa_set_device": (c_int, [c_int]),
     "fa_malloc": (c_void_p, [c_size_t]),
     "fa_malloc_host": (c_void_p, [c_size_t]),
+    "fa_malloc_async": (c_void_p, [c_size_t, c_void_p]),
+    "fa_free_async": (c_int, [c_void_p, c_void_p]),
+    "fa_memset_async": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
     "fa_free": (c_int, [c_void_p]),
     "fa_free_host": (c_int, [c_void_p]),
     "fa_memset": (c_int, [c_void_p, c_int, c_size_t]),
@@ -102,6 +105,11 @@ SYMBOLS["combine"] = {
                          c_int, c_int]),
     "tensorReduce": (None, [_f32, _i32, _i32, c_int, _f32, _i32, _i32, c_int, c_double, c_int, c_int]),
     "MatrixMultiply": (None, [_f32, _i32, _i32, _f32, _i32, _i32, _f32, _i32, _i32, c_int, c_int, c_int]),
+    "fa_map_dev": (c_int, [c_void_p, _i32, _i32, c_int, c_void_p, _i32, _i32, c_int, c_int, c_void_p]),
+    "fa_zip_dev": (c_int, [c_void_p, _i32, _i32, c_int, c_void_p, _i32, _i32, c_int, c_void_p, _i32, _i32, c_int, c_int,
+                           c_void_p]),
+    "fa_reduce_dev": (c_int, [c_void_p, _i32, _i32, c_void_p, _i32, _i32, c_int, c_int, c_double, c_int, c_void_p]),
+    "fa_matmul_dev": (c_int, [c_void_p, _i32, _i32, c_void_p, _i32, _i32, c_void_p, _i32, _i32, c_void_p]),
 }
 
 _libs = {}

@@ -346,4 +346,98 @@ void MatrixMultiply(float* out, int* out_shape, int* out_strides, float* a_stora
   CB_CUDA(cudaStreamSynchronize(0));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-pointer variants (additive; SURVEY.md 8(f)-1 "kept device-resident"): same kernels, operands
+// already in HBM, shapes / strides as host int arrays, asynchronous on `stream`.  With these a tensor
+// library can keep its storage on the GPU and pay no PCIe round trip per op.
+// ---------------------------------------------------------------------------------------------
+int fa_map_dev(float* out, const int* out_shape, const int* out_strides, int out_nd, const float* in,
+               const int* in_shape, const int* in_strides, int in_nd, int fn_id, fa_stream_t stream) {
+  clear_error();
+  Layout lo, li;
+  if (!out || !in || !make_layout(&lo, out_shape, out_strides, out_nd) || !make_layout(&li, in_shape, in_strides, in_nd) ||
+      in_nd > out_nd)
+    return set_error(FA_ERR_INVALID, "fa_map_dev: bad arguments (ranks %d -> %d, max %d)", in_nd, out_nd, kMaxDims);
+  long long n = 1;
+  for (int i = 0; i < lo.nd; ++i) n *= lo.shape[i];
+  if (n <= 0) return FA_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool fast = same_shape(lo, li) && is_contiguous(lo) && is_contiguous(li) && (n % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;
+  if (fast)
+    map_contig_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(out),
+                                                            reinterpret_cast<const float4*>(in), n / 4, fn_id);
+  else
+    map_kernel<<<grid_for(n, 256), 256, 0, st>>>(out, lo, in, li, n, fn_id);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+int fa_zip_dev(float* out, const int* out_shape, const int* out_strides, int out_nd, const float* a, const int* a_shape,
+               const int* a_strides, int a_nd, const float* b, const int* b_shape, const int* b_strides, int b_nd,
+               int fn_id, fa_stream_t stream) {
+  clear_error();
+  Layout lo, la, lb;
+  if (!out || !a || !b || !make_layout(&lo, out_shape, out_strides, out_nd) || !make_layout(&la, a_shape, a_strides, a_nd) ||
+      !make_layout(&lb, b_shape, b_strides, b_nd) || a_nd > out_nd || b_nd > out_nd)
+    return set_error(FA_ERR_INVALID, "fa_zip_dev: bad arguments (ranks %d, %d -> %d)", a_nd, b_nd, out_nd);
+  long long n = 1;
+  for (int i = 0; i < lo.nd; ++i) n *= lo.shape[i];
+  if (n <= 0) return FA_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool fast = same_shape(lo, la) && same_shape(lo, lb) && is_contiguous(lo) && is_contiguous(la) &&
+                    is_contiguous(lb) && (n % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (fast)
+    zip_contig_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(out),
+                                                            reinterpret_cast<const float4*>(a),
+                                                            reinterpret_cast<const float4*>(b), n / 4, fn_id);
+  else
+    zip_kernel<<<grid_for(n, 256), 256, 0, st>>>(out, lo, a, la, b, lb, n, fn_id);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+int fa_reduce_dev(float* out, const int* out_shape, const int* out_strides, const float* a, const int* a_shape,
+                  const int* a_strides, int nd, int reduce_dim, double reduce_value, int fn_id, fa_stream_t stream) {
+  clear_error();
+  Layout lo, la;
+  if (!out || !a || !make_layout(&lo, out_shape, out_strides, nd) || !make_layout(&la, a_shape, a_strides, nd) ||
+      reduce_dim < 0 || reduce_dim >= nd)
+    return set_error(FA_ERR_INVALID, "fa_reduce_dev: bad rank %d / dim %d", nd, reduce_dim);
+  long long n = 1;
+  for (int i = 0; i < lo.nd; ++i) n *= lo.shape[i];
+  if (n <= 0) return FA_OK;
+  reduce_kernel<<<grid_for(n * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      out, lo, a, la, n, reduce_dim, static_cast<float>(reduce_value), fn_id);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+// out (batch, m, p) = a (batch | 1, m, n) @ b (batch | 1, n, p), 3-D shapes and element strides
+int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, const float* a, const int* a_shape,
+                  const int* a_strides, const float* b, const int* b_shape, const int* b_strides, fa_stream_t stream) {
+  clear_error();
+  if (!out || !a || !b) return set_error(FA_ERR_INVALID, "fa_matmul_dev: null pointer");
+  const int batch = out_shape[0], m = out_shape[1], p = out_shape[2], n = a_shape[2];
+  if (batch <= 0 || m <= 0 || p <= 0 || n <= 0 || b_shape[1] != n || a_shape[1] != m || b_shape[2] != p ||
+      (a_shape[0] != batch && a_shape[0] != 1) || (b_shape[0] != batch && b_shape[0] != 1) || batch > 65535)
+    return set_error(FA_ERR_INVALID, "fa_matmul_dev: bad shapes (%d,%d,%d) @ (%d,%d,%d) -> (%d,%d,%d)", a_shape[0],
+                     a_shape[1], a_shape[2], b_shape[0], b_shape[1], b_shape[2], batch, m, p);
+  MMStrides st;
+  st.ab = (a_shape[0] > 1) ? a_strides[0] : 0;
+  st.am = a_strides[1], st.ak = a_strides[2];
+  st.bb = (b_shape[0] > 1) ? b_strides[0] : 0;
+  st.bk = b_strides[1], st.bn = b_strides[2];
+  st.ob = out_strides[0], st.om = out_strides[1], st.on = out_strides[2];
+  dim3 grid((p + 63) / 64, (m + 63) / 64, batch);
+  matmul_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, a, b, st, m, p, n);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
 }  // extern "C"

@@ -107,6 +107,39 @@ void* fa_malloc_host(size_t bytes) {
   }
   return p;
 }
+// Stream-ordered allocation from the device's default memory pool (release threshold raised so freed blocks stay
+// cached): what a device-resident tensor library allocates its per-op outputs from.
+void* fa_malloc_async(size_t bytes, fa_stream_t stream) {
+  fa::clear_error();
+  static bool tuned[fa::ScratchPool::kMaxDev] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < fa::ScratchPool::kMaxDev && !tuned[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned[dev] = true;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    fa::set_error(FA_ERR_CUDA, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+int fa_free_async(void* p, fa_stream_t stream) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaFreeAsync(p, reinterpret_cast<cudaStream_t>(stream)));
+  return FA_OK;
+}
+int fa_memset_async(void* p, int byte, size_t bytes, fa_stream_t stream) {
+  fa::clear_error();
+  FA_CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return FA_OK;
+}
 int fa_free(void* p) {
   fa::clear_error();
   FA_CUDA_CHECK(cudaFree(p));

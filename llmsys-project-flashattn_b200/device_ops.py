@@ -1,0 +1,309 @@
+"""``DeviceKernelOps`` -- the same operator surface as ``CudaKernelOps`` with tensor storage RESIDENT IN HBM.
+
+SURVEY.md 8(f)-1: in the reference every op is a host-pointer call (cudaMalloc + H2D + kernel + D2H + cudaFree,
+minitorch/cuda_kernel_ops.py:60-437 / src/combine.cu:315-580), so once attention is fused the PCIe round trips of
+the plumbing dominate a training step.  Here a tensor's ``_tensor._storage`` is a ``DeviceStorage`` (fp32, from
+the stream-ordered pool), every op calls the ``*_dev`` entry point of the C ABI on the default stream, and data
+crosses PCIe only in ``tensor_from_numpy`` / ``to_numpy``.  Bind it with ``TensorBackend(DeviceKernelOps)``; the
+autograd nodes and the MultiHeadAttention / DecoderLM modules are unchanged.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .cuda_kernel_ops import _fn_id, _i32, shape_broadcast
+
+datatype = np.float32
+
+
+def _fa():
+    return _lib.load("flashattention_kernel")
+
+
+class DeviceStorage:
+    """Flat fp32 device buffer; freed (stream-ordered) on garbage collection."""
+
+    __slots__ = ("ptr", "size")
+
+    def __init__(self, size: int):
+        self.size = int(size)
+        lib = _fa()
+        self.ptr = lib.fa_malloc_async(max(self.size, 1) * 4, None)
+        if not self.ptr:
+            _lib.check(lib)
+            raise MemoryError(f"fa_malloc_async({self.size * 4}) failed")
+
+    @classmethod
+    def from_numpy(cls, arr) -> "DeviceStorage":
+        host = np.ascontiguousarray(arr, dtype=datatype).reshape(-1)
+        out = cls(host.size)
+        if host.size:
+            lib = _fa()
+            _lib.check(lib, lib.fa_h2d(out.ptr, host.ctypes.data_as(ctypes.c_void_p), host.size * 4))
+        return out
+
+    def to_numpy(self) -> np.ndarray:
+        host = np.empty(self.size, dtype=datatype)
+        if self.size:
+            lib = _fa()
+            _lib.check(lib, lib.fa_d2h(host.ctypes.data_as(ctypes.c_void_p), self.ptr, self.size * 4))
+        return host
+
+    def __len__(self):
+        return self.size
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _fa().fa_free_async(self.ptr, None)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _st(t) -> DeviceStorage:
+    return t._tensor._storage
+
+
+def _layout(t):
+    d = t._tensor
+    return _i32(d.shape), _i32(d.strides)
+
+
+def _size(t) -> int:
+    return int(np.prod(t.shape)) if len(t.shape) else 1
+
+
+def _bf16_copy(t):
+    """bf16 image of a contiguous fp32 tensor (device scratch, 2 bytes per element)."""
+    lib = _fa()
+    n = _size(t)
+    buf = DeviceStorage((n + 1) // 2)
+    _lib.check(lib, lib.fa_cast_f32_to_bf16_dev(_st(t).ptr, buf.ptr, n, None))
+    return buf
+
+
+class DeviceKernelOps:
+    cuda = True
+    device_resident = True
+    flash_mode = "fp32"       # "bf16": tcgen05 tensor-core kernels for head_dim 64 / 128 (operands rounded on device)
+
+    # ---- storage hooks used by HostTensor ------------------------------------------------------------------
+    @staticmethod
+    def to_storage(x):
+        return x if isinstance(x, DeviceStorage) else DeviceStorage.from_numpy(x)
+
+    @staticmethod
+    def zeros_storage(n: int):
+        st = DeviceStorage(n)
+        lib = _fa()
+        _lib.check(lib, lib.fa_memset_async(st.ptr, 0, max(int(n), 1) * 4, None))
+        return st
+
+    @staticmethod
+    def storage_to_numpy(st) -> np.ndarray:
+        return st.to_numpy()
+
+    # ---- map / zip / reduce / matmul -------------------------------------------------------------------------
+    @staticmethod
+    def map(fn):
+        fn_id = _fn_id(fn)
+
+        def ret(a, out=None):
+            lib = _lib.load("combine")
+            if out is None:
+                out = a.zeros(a.shape)
+            osh, ost = _layout(out)
+            ash, ast = _layout(a)
+            _lib.check(lib, lib.fa_map_dev(_st(out).ptr, osh, ost, len(osh), _st(a).ptr, ash, ast, len(ash), fn_id, None))
+            return out
+
+        return ret
+
+    @staticmethod
+    def zip(fn):
+        fn_id = _fn_id(fn)
+
+        def ret(a, b):
+            lib = _lib.load("combine")
+            out = a.zeros(shape_broadcast(a.shape, b.shape))
+            osh, ost = _layout(out)
+            ash, ast = _layout(a)
+            bsh, bst = _layout(b)
+            _lib.check(lib, lib.fa_zip_dev(_st(out).ptr, osh, ost, len(osh), _st(a).ptr, ash, ast, len(ash), _st(b).ptr,
+                                           bsh, bst, len(bsh), fn_id, None))
+            return out
+
+        return ret
+
+    @staticmethod
+    def reduce(fn, start: float = 0.0):
+        fn_id = _fn_id(fn)
+
+        def ret(a, dim: int):
+            lib = _lib.load("combine")
+            out_shape = list(a.shape)
+            out_shape[dim] = 1
+            out = a.zeros(tuple(out_shape))
+            osh, ost = _layout(out)
+            ash, ast = _layout(a)
+            _lib.check(lib, lib.fa_reduce_dev(_st(out).ptr, osh, ost, _st(a).ptr, ash, ast, len(ash), int(dim),
+                                              float(start), fn_id, None))
+            return out
+
+        return ret
+
+    @staticmethod
+    def matrix_multiply(a, b):
+        """Same shape handling as CudaKernelOps.matrix_multiply (minitorch/cuda_kernel_ops.py:343-437); operands
+        are used in place through their strides (transposed views need no copy)."""
+        lib = _lib.load("combine")
+        if a.shape[-1] != b.shape[-2]:
+            raise AssertionError(f"matmul inner dims differ: {a.shape} @ {b.shape}")
+        lead = shape_broadcast(a.shape[:-2], b.shape[:-2])
+        ls = list(lead) + [a.shape[-2], b.shape[-1]]
+
+        def as3(t):
+            if len(t.shape) == 2:
+                return (1,) + tuple(t.shape), (0,) + tuple(t._tensor.strides), t
+            if len(t.shape) == 3:
+                return tuple(t.shape), tuple(t._tensor.strides), t
+            t = t.contiguous()
+            nb = int(np.prod(t.shape[:-2]))
+            return (nb, t.shape[-2], t.shape[-1]), (t.shape[-2] * t.shape[-1], t.shape[-1], 1), t
+
+        ash, ast, a = as3(a)
+        bsh, bst, b = as3(b)
+        nb = int(np.prod(lead)) if lead else 1
+        if ash[0] not in (1, nb) or bsh[0] not in (1, nb):
+            raise IndexError(f"cannot broadcast matmul batches {a.shape} @ {b.shape}")
+        out = a.zeros(tuple(ls))
+        m, p = ls[-2], ls[-1]
+        lib_rc = lib.fa_matmul_dev(_st(out).ptr, _i32((nb, m, p)), _i32((m * p, p, 1)), _st(a).ptr, _i32(ash), _i32(ast),
+                                   _st(b).ptr, _i32(bsh), _i32(bst), None)
+        _lib.check(lib, lib_rc)
+        return out
+
+    # ---- flash attention ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _desc(B, nh, N, d, causal, bf16):
+        a = _lib.fa_attn_desc()
+        a.B, a.H, a.N, a.d = B, nh, N, d
+        a.dtype = _lib.FA_DTYPE_BF16 if bf16 else _lib.FA_DTYPE_F32
+        a.causal = int(bool(causal))
+        return a
+
+    @staticmethod
+    def _flash_fw(Q, K, V, causal):
+        lib = _fa()
+        B, nh, N, d = Q.shape
+        Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+        O, m, l = Q.zeros((B, nh, N, d)), Q.zeros((B, nh, N)), Q.zeros((B, nh, N))
+        bf16 = DeviceKernelOps.flash_mode == "bf16" and d in (64, 128)
+        a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16)
+        if bf16:
+            q, k, v = (_bf16_copy(t) for t in (Q, K, V))
+            o = DeviceStorage((_size(O) + 1) // 2)
+            _lib.check(lib, lib.fa_flash_fwd_dev(ctypes.byref(a), q.ptr, k.ptr, v.ptr, o.ptr, _st(m).ptr, _st(l).ptr, None))
+            _lib.check(lib, lib.fa_cast_bf16_to_f32_dev(o.ptr, _st(O).ptr, _size(O), None))
+        else:
+            _lib.check(lib, lib.fa_flash_fwd_dev(ctypes.byref(a), _st(Q).ptr, _st(K).ptr, _st(V).ptr, _st(O).ptr,
+                                                 _st(m).ptr, _st(l).ptr, None))
+        return O, m, l
+
+    @staticmethod
+    def _flash_bw(Q, K, V, O, dO, m, l, causal):
+        lib = _fa()
+        B, nh, N, d = Q.shape
+        Q, K, V, O, dO, m, l = (t.contiguous() for t in (Q, K, V, O, dO, m, l))
+        grads = tuple(Q.zeros((B, nh, N, d)) for _ in range(3))
+        bf16 = DeviceKernelOps.flash_mode == "bf16" and d in (64, 128)
+        a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16)
+        if bf16:
+            q, k, v, o, do = (_bf16_copy(t) for t in (Q, K, V, O, dO))
+            g16 = [DeviceStorage((_size(Q) + 1) // 2) for _ in range(3)]
+            _lib.check(lib, lib.fa_flash_bwd_dev(ctypes.byref(a), q.ptr, k.ptr, v.ptr, o.ptr, do.ptr, _st(m).ptr,
+                                                 _st(l).ptr, g16[0].ptr, g16[1].ptr, g16[2].ptr, None))
+            for src, dst in zip(g16, grads):
+                _lib.check(lib, lib.fa_cast_bf16_to_f32_dev(src.ptr, _st(dst).ptr, _size(dst), None))
+        else:
+            _lib.check(lib, lib.fa_flash_bwd_dev(ctypes.byref(a), _st(Q).ptr, _st(K).ptr, _st(V).ptr, _st(O).ptr,
+                                                 _st(dO).ptr, _st(m).ptr, _st(l).ptr, _st(grads[0]).ptr,
+                                                 _st(grads[1]).ptr, _st(grads[2]).ptr, None))
+        return grads
+
+    @staticmethod
+    def flash_attention_fw(Q, K, V):
+        return DeviceKernelOps._flash_fw(Q, K, V, False)
+
+    @staticmethod
+    def flash_attention_bw(Q, K, V, O, dO, m, l):
+        return DeviceKernelOps._flash_bw(Q, K, V, O, dO, m, l, False)
+
+    @staticmethod
+    def flash_attention_causal_fw(Q, K, V):
+        return DeviceKernelOps._flash_fw(Q, K, V, True)
+
+    @staticmethod
+    def flash_attention_causal_bw(Q, K, V, O, dO, m, l):
+        return DeviceKernelOps._flash_bw(Q, K, V, O, dO, m, l, True)
+
+    # ---- fused softmax / layernorm -----------------------------------------------------------------------------
+    @staticmethod
+    def attn_softmax_fw(inp, mask, mask_future: bool = False):
+        """In place on a contiguous `inp` (returns it), like the reference (:440-468)."""
+        lib = _lib.load("softmax_kernel")
+        B, nhead, from_len, to_len = inp.shape
+        assert inp._tensor.is_contiguous(), "attn_softmax_fw works in place on a contiguous tensor"
+        mptr = None
+        if mask is not None:
+            mask = mask.contiguous()
+            if _size(mask) < B * to_len:
+                raise ValueError("attn_softmax_fw: mask must hold (batch, to_len) additive values")
+            mptr = _st(mask).ptr
+        _lib.check(lib, lib.fa_attn_softmax_dev(_st(inp).ptr, mptr, B, nhead, from_len, to_len, int(bool(mask_future)),
+                                                None))
+        return inp
+
+    @staticmethod
+    def attn_softmax_bw(out_grad, soft_inp):
+        lib = _lib.load("softmax_kernel")
+        rows = out_grad.shape[0] * out_grad.shape[1] * out_grad.shape[2]
+        assert out_grad._tensor.is_contiguous()
+        soft_inp = soft_inp.contiguous()
+        _lib.check(lib, lib.fa_attn_softmax_bw_dev(_st(out_grad).ptr, _st(soft_inp).ptr, rows, soft_inp.shape[3], None))
+        return out_grad, soft_inp
+
+    @staticmethod
+    def layernorm_fw(inp, gamma, beta):
+        lib = _lib.load("layernorm_kernel")
+        rows, hidden = inp.shape
+        ln_res, var, means = inp.zeros(inp.shape), inp.zeros((rows,)), inp.zeros((rows,))
+        inp, gamma, beta = inp.contiguous(), gamma.contiguous(), beta.contiguous()
+        _lib.check(lib, lib.fa_layernorm_dev(_st(ln_res).ptr, _st(var).ptr, _st(means).ptr, _st(inp).ptr, _st(gamma).ptr,
+                                             _st(beta).ptr, rows, hidden, None))
+        return ln_res, var, means
+
+    @staticmethod
+    def layernorm_bw(out_grad, inp, gamma, beta, var, mean):
+        lib = _lib.load("layernorm_kernel")
+        rows, hidden = inp.shape
+        gamma_grad, beta_grad = gamma.zeros((1, gamma.shape[0])), beta.zeros((1, beta.shape[0]))
+        inp_grad = inp.zeros(inp.shape)
+        out_grad, inp, gamma, beta, var, mean = (t.contiguous() for t in (out_grad, inp, gamma, beta, var, mean))
+        _lib.check(lib, lib.fa_layernorm_bw_dev(_st(gamma_grad).ptr, _st(beta_grad).ptr, _st(inp_grad).ptr,
+                                                _st(out_grad).ptr, _st(inp).ptr, _st(gamma).ptr, _st(beta).ptr,
+                                                _st(var).ptr, _st(mean).ptr, rows, hidden, None))
+        return inp_grad, gamma_grad, beta_grad
+
+    @staticmethod
+    def set_flash_mode(mode: str) -> None:
+        assert mode in ("fp32", "bf16")
+        DeviceKernelOps.flash_mode = mode
+
+    @staticmethod
+    def get_flash_mode() -> str:
+        return DeviceKernelOps.flash_mode

@@ -28,6 +28,8 @@ class TensorBackend:
     def __init__(self, ops=CudaKernelOps):
         self.ops = ops
         self.cuda = getattr(ops, "cuda", False)
+        # storage lives in HBM (DeviceKernelOps) instead of host numpy memory (CudaKernelOps, like the reference)
+        self.device = getattr(ops, "device_resident", False)
         if hasattr(ops, "map"):   # map / zip / reduce / matmul over combine.so, same attribute names as the reference
             for name in ("neg", "sigmoid", "relu", "log", "exp", "id", "inv", "tanh"):
                 setattr(self, name + "_map", ops.map(name))
@@ -109,12 +111,19 @@ class HostTensor:
     # ---- construction -------------------------------------------------------------
     @staticmethod
     def make(storage, shape, strides=None, backend=None) -> "HostTensor":
-        st = np.ascontiguousarray(storage, dtype=datatype).reshape(-1)
+        backend = backend if backend is not None else default_backend()
+        if backend.device:
+            st = backend.ops.to_storage(storage)
+        else:
+            st = np.ascontiguousarray(storage, dtype=datatype).reshape(-1)
         return HostTensor(_Data(st, shape, strides), backend)
 
     def zeros(self, shape=None) -> "HostTensor":
         shape = self.shape if shape is None else tuple(shape)
-        return HostTensor.make(np.zeros(int(np.prod(shape)), dtype=datatype), shape, backend=self.backend)
+        n = int(np.prod(shape)) if len(shape) else 1
+        if self.backend.device:
+            return HostTensor(_Data(self.backend.ops.zeros_storage(n), shape), self.backend)
+        return HostTensor.make(np.zeros(n, dtype=datatype), shape, backend=self.backend)
 
     def detach(self) -> "HostTensor":
         return HostTensor(self._tensor, self.backend)
@@ -137,8 +146,11 @@ class HostTensor:
     def contiguous(self) -> "HostTensor":
         if self._tensor.is_contiguous():
             return self
-        arr = np.ascontiguousarray(self._tensor.view_array())
-        out = HostTensor.make(arr.reshape(-1), self.shape, backend=self.backend)
+        if self.backend.device:
+            out = self.f.id_map(self.detach())      # strided read -> fresh contiguous buffer, on the device
+        else:
+            arr = np.ascontiguousarray(self._tensor.view_array())
+            out = HostTensor.make(arr.reshape(-1), self.shape, backend=self.backend)
         if self.requires_grad():
             out._node = (_Contiguous, None, (self,))
         return out
@@ -158,6 +170,10 @@ class HostTensor:
         return out
 
     def to_numpy(self) -> np.ndarray:
+        if self.backend.device:
+            host = self.backend.ops.storage_to_numpy(self._tensor._storage)
+            return np.array(np.lib.stride_tricks.as_strided(host, self.shape, tuple(s * 4 for s in self._tensor.strides)),
+                            dtype=datatype)
         return np.array(self._tensor.view_array(), dtype=datatype)
 
     # ---- fused ops (minitorch/tensor.py:424-436) ------------------------------------
@@ -267,6 +283,8 @@ class HostTensor:
 
 
 def _add(a: HostTensor, b: HostTensor) -> HostTensor:
+    if a.backend.device:
+        return a.f.add_zip(a, b)
     return tensor_from_numpy(a.to_numpy() + b.to_numpy(), backend=a.backend)
 
 
@@ -463,8 +481,17 @@ def logsumexp(x: HostTensor, dim: int) -> HostTensor:
 
 
 def one_hot(x: HostTensor, num_classes: int) -> HostTensor:
-    """minitorch/nn.py:212-222: a host-side index-to-row expansion (np.eye lookup), no arithmetic."""
-    return tensor_from_numpy(np.eye(num_classes, dtype=datatype)[x.to_numpy().astype(int)], backend=x.backend)
+    """minitorch/nn.py:212-222 (an np.eye row lookup there).  Host storage: the rows are written directly;
+    device storage: eq_zip of the indices against a class-id row, so the (n, C) matrix is born in HBM."""
+    if x.backend.device:
+        n = x.size
+        idx = x.contiguous().view(n, 1)
+        classes = tensor_from_numpy(np.arange(num_classes, dtype=datatype).reshape(1, num_classes), backend=x.backend)
+        return x.f.eq_zip(idx, classes).view(*x.shape, num_classes)
+    idx = x.to_numpy().astype(np.int64).reshape(-1)
+    hot = np.zeros((idx.size, num_classes), dtype=datatype)
+    hot[np.arange(idx.size), idx] = 1.0
+    return tensor_from_numpy(hot.reshape(*x.shape, num_classes), backend=x.backend)
 
 
 def softmax_loss(logits: HostTensor, target: HostTensor) -> HostTensor:
@@ -488,7 +515,11 @@ class Attn_Softmax(Function):
     @staticmethod
     def backward(ctx, out_grad):
         soft, _mask = ctx.saved_values
-        g = tensor_from_numpy(out_grad.to_numpy(), backend=out_grad.backend)  # bw kernel is in place
+        # the bw kernel works in place: hand it a private contiguous copy of the incoming gradient
+        if out_grad.backend.device:
+            g = out_grad.f.id_map(out_grad)
+        else:
+            g = tensor_from_numpy(out_grad.to_numpy(), backend=out_grad.backend)
         g, _ = out_grad.f.attn_softmax_bw(g, soft)
         return g, None
 

@@ -18,7 +18,8 @@ from tests.test_host_modules import decoder_loss  # noqa: E402
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-    backend = fb.default_backend()
+    residency = sys.argv[2] if len(sys.argv) > 2 else "host"      # "host": reference-style host storage; "device": HBM
+    backend = fb.TensorBackend(fb.DeviceKernelOps) if residency == "device" else fb.default_backend()
     n_vocab, n_embd, n_head, n_pos = 10000, 256, 8, 40
     rng = np.random.default_rng(11111)
     ids = rng.integers(0, n_vocab, (B, n_pos))
@@ -43,6 +44,7 @@ def main():
             loss[branch] = float(total.to_numpy().reshape(-1)[0])
     for branch in models:
         print(json.dumps({"workload": f"DecoderLM cfg2 step (fwd + loss + bwd), batch {B}, seq 39, fp32",
+                          "storage": residency,
                           "attention": branch, "step_s_best": min(times[branch]), "step_s_all": times[branch],
                           "loss": loss[branch]}), flush=True)
     fb.CudaKernelOps.set_flash_mode("fp32")
