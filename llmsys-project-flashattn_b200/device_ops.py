@@ -189,21 +189,58 @@ class DeviceKernelOps:
 
     # ---- flash attention ---------------------------------------------------------------------------------------
     @staticmethod
-    def _desc(B, nh, N, d, causal, bf16):
+    def _desc(B, nh, N, d, causal, bf16, strides=None):
         a = _lib.fa_attn_desc()
         a.B, a.H, a.N, a.d = B, nh, N, d
         a.dtype = _lib.FA_DTYPE_BF16 if bf16 else _lib.FA_DTYPE_F32
         a.causal = int(bool(causal))
+        if strides is not None:
+            a.stride_b, a.stride_h, a.stride_n = strides
         return a
+
+    @staticmethod
+    def _shared_layout(tensors):
+        """(stride_b, stride_h, stride_n) when every tensor is the SAME dense, unit-inner-stride view -- e.g. the
+        permuted (B, nh, N, d) views of (B, N, nh, d) storage that project_to_query_key_value hands over
+        (modules_transfomer.py:87-100).  The kernels then consume them in place (TMA descriptors / index math carry
+        the strides): no .contiguous() copies on either side of the attention core."""
+        first = tensors[0]._tensor
+        st = first.strides
+        if st[3] != 1 or len(_st(tensors[0])) != _size(tensors[0]):
+            return None
+        dense = sorted(zip(st, first.shape), reverse=True)       # a permutation of a packed buffer?
+        acc = 1
+        for stride, extent in reversed(dense):
+            if extent != 1 and stride != acc:
+                return None
+            acc *= extent
+        for t in tensors[1:]:
+            if t._tensor.strides != st or t.shape != tensors[0].shape or len(_st(t)) != _size(t):
+                return None
+        if any(x % 8 for x in st[:3]):                           # TMA wants 16-byte multiples
+            return None
+        return st[0], st[1], st[2]
+
+    @staticmethod
+    def _like(t, strides4):
+        """Uninitialised-but-zeroed tensor with t's shape laid out with the given strides."""
+        from .tensor import HostTensor, _Data
+        st = DeviceKernelOps.zeros_storage(_size(t))
+        return HostTensor(_Data(st, t.shape, strides4), t.backend)
 
     @staticmethod
     def _flash_fw(Q, K, V, causal):
         lib = _fa()
         B, nh, N, d = Q.shape
-        Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
-        O, m, l = Q.zeros((B, nh, N, d)), Q.zeros((B, nh, N)), Q.zeros((B, nh, N))
+        lay = DeviceKernelOps._shared_layout((Q, K, V))
+        if lay is None:
+            Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+            O = Q.zeros((B, nh, N, d))
+        else:
+            O = DeviceKernelOps._like(Q, Q._tensor.strides)
+        m, l = Q.zeros((B, nh, N)), Q.zeros((B, nh, N))
         bf16 = DeviceKernelOps.flash_mode == "bf16" and d in (64, 128)
-        a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16)
+        a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16, lay)
         if bf16:
             q, k, v = (_bf16_copy(t) for t in (Q, K, V))
             o = DeviceStorage((_size(O) + 1) // 2)
@@ -218,10 +255,15 @@ class DeviceKernelOps:
     def _flash_bw(Q, K, V, O, dO, m, l, causal):
         lib = _fa()
         B, nh, N, d = Q.shape
-        Q, K, V, O, dO, m, l = (t.contiguous() for t in (Q, K, V, O, dO, m, l))
-        grads = tuple(Q.zeros((B, nh, N, d)) for _ in range(3))
+        m, l = m.contiguous(), l.contiguous()
+        lay = DeviceKernelOps._shared_layout((Q, K, V, O, dO))
+        if lay is None:
+            Q, K, V, O, dO = (t.contiguous() for t in (Q, K, V, O, dO))
+            grads = tuple(Q.zeros((B, nh, N, d)) for _ in range(3))
+        else:
+            grads = tuple(DeviceKernelOps._like(Q, Q._tensor.strides) for _ in range(3))
         bf16 = DeviceKernelOps.flash_mode == "bf16" and d in (64, 128)
-        a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16)
+        a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16, lay)
         if bf16:
             q, k, v, o, do = (_bf16_copy(t) for t in (Q, K, V, O, dO))
             g16 = [DeviceStorage((_size(Q) + 1) // 2) for _ in range(3)]
