@@ -188,6 +188,20 @@ int fa_reduce_dev(float* out, const int* out_shape, const int* out_strides, cons
                   const int* a_strides, int nd, int reduce_dim, double reduce_value, int fn_id, fa_stream_t stream);
 int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, const float* a, const int* a_shape,
                   const int* a_strides, const float* b, const int* b_shape, const int* b_strides, fa_stream_t stream);
+/* Embedding lookup and softmax cross-entropy without one-hot matmuls (additive; the reference
+ * builds (tokens, vocab) one-hot matrices, minitorch/modules_basic.py:55-71 and nn.py:251-271, and only declares
+ * fused kernels, src/includes/kernels.h:196-215).  ids / targets are fp32 tensors holding integers.
+ *   fa_embedding_fw_dev:    out (n,E) = W (V,E) rows selected by ids (n)          == one_hot(ids) @ W
+ *   fa_embedding_bw_dev:    dW (V,E)  = sum of dout rows per id, ascending order  == one_hot(ids)^T @ dout, deterministic
+ *   fa_softmax_xent_fw_dev: loss (n) = logsumexp(logits (n,C)) - logits[i, t_i]; lse (n) saved for the backward;
+ *                           logsumexp = max + log(sum + 1e-6), minitorch's log (operators.py:107-110)
+ *   fa_softmax_xent_bw_dev: dlogits = dloss[i] * (exp(logits - lse[i]) - [j == t_i]) */
+int fa_embedding_fw_dev(float* out, const float* ids, const float* W, long long n, int V, int E, fa_stream_t stream);
+int fa_embedding_bw_dev(float* dW, const float* ids, const float* dout, long long n, int V, int E, fa_stream_t stream);
+int fa_softmax_xent_fw_dev(float* loss, float* lse, const float* logits, const float* targets, long long n, int C,
+                           fa_stream_t stream);
+int fa_softmax_xent_bw_dev(float* dlogits, const float* dloss, const float* logits, const float* targets,
+                           const float* lse, long long n, int C, fa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ from . import _lib, device, sharding
 from ._lib import FlashAttnError
 from .cuda_kernel_ops import CudaKernelOps
 from .device_ops import DeviceKernelOps, DeviceStorage
-from .tensor import (Attn_Softmax, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
+from .tensor import (Attn_Softmax, EmbeddingLookup, SoftmaxCrossEntropy, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
                      default_backend, logsumexp, one_hot, softmax, softmax_loss, GELU,
                      tensor_from_numpy)
 from . import modules_transformer
@@ -23,4 +23,4 @@ from .modules_transformer import (DecoderLM, Dropout, Embedding, FeedForward, Fu
 __all__ = ["CudaKernelOps", "DeviceKernelOps", "DeviceStorage", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
            "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding", "softmax", "modules_transformer",
            "MultiHeadAttention", "Linear", "Dropout", "DecoderLM", "TransformerLayer", "FeedForward", "Embedding",
-           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU"]
+           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU", "EmbeddingLookup", "SoftmaxCrossEntropy"]

@@ -176,6 +176,107 @@ __global__ void __launch_bounds__(256) matmul_kernel(float* __restrict__ out, co
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// embedding lookup and softmax cross-entropy without the one-hot matmuls
+// (minitorch/modules_basic.py:55-71 builds a (tokens, vocab) one-hot and multiplies; nn.py:251-271 likewise;
+// the reference only DECLARES fused versions, src/includes/kernels.h:196-215).  Token ids / targets are fp32
+// tensors, as minitorch stores them.  All HBM-bound row kernels: 128-bit accesses where the row allows.
+// ---------------------------------------------------------------------------------------------
+// out[i, :] = W[ids[i], :]                      (== one_hot(ids) @ W exactly)
+__global__ void embedding_fw_kernel(float* __restrict__ out, const float* __restrict__ ids, const float* __restrict__ W,
+                                    long long n, int V, int E) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long i = warp0; i < n; i += nwarps) {
+    const int v = static_cast<int>(ids[i]);
+    float* o = out + i * E;
+    if (v < 0 || v >= V) {               // np.eye(V)[id] would raise; here: a zero row
+      for (int e = lane; e < E; e += 32) o[e] = 0.f;
+      continue;
+    }
+    const float* w = W + static_cast<long long>(v) * E;
+    if ((E & 3) == 0) {
+      for (int e = lane * 4; e < E; e += 128)
+        *reinterpret_cast<float4*>(o + e) = __ldg(reinterpret_cast<const float4*>(w + e));
+    } else {
+      for (int e = lane; e < E; e += 32) o[e] = __ldg(w + e);
+    }
+  }
+}
+// dW[v, :] = sum over tokens i with ids[i] == v of dout[i, :], tokens visited in ascending order: bitwise
+// deterministic (== one_hot(ids)^T @ dout).  One CTA per vocabulary row; a warp-wide ballot finds the matches.
+__global__ void embedding_bw_kernel(float* __restrict__ dW, const float* __restrict__ ids, const float* __restrict__ dout,
+                                    long long n, int V, int E) {
+  for (int v = blockIdx.x; v < V; v += gridDim.x) {
+    const float fv = static_cast<float>(v);
+    for (int e0 = 0; e0 < E; e0 += blockDim.x) {
+      const int e = e0 + threadIdx.x;
+      float acc = 0.f;
+      for (long long base = 0; base < n; base += 32) {
+        const long long i = base + (threadIdx.x & 31);
+        const bool hit = (i < n) && (__ldg(ids + i) == fv);
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          if (e < E) acc += __ldg(dout + (base + b) * E + e);
+        }
+      }
+      if (e < E) dW[static_cast<long long>(v) * E + e] = acc;
+    }
+  }
+}
+// loss[i] = logsumexp(x[i, :]) - x[i, t_i], lse[i] saved for the backward.  logsumexp = max + log(sum + 1e-6):
+// minitorch's log adds EPS = 1e-6 (operators.py:107-110), so the composed reference computes exactly this.
+__global__ void __launch_bounds__(256) softmax_xent_fw_kernel(float* __restrict__ loss, float* __restrict__ lse,
+                                                               const float* __restrict__ x, const float* __restrict__ tgt,
+                                                               long long n, int C) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+    const float* r = x + i * C;
+    float mx = -FLT_MAX;
+    for (int j = threadIdx.x; j < C; j += 256) mx = fmaxf(mx, __ldg(r + j));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int j = threadIdx.x; j < C; j += 256) s += expf(__ldg(r + j) - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      const float l = mx + logf(tot + 1e-6f);
+      const int t = static_cast<int>(tgt[i]);
+      lse[i] = l;
+      loss[i] = l - ((t >= 0 && t < C) ? r[t] : 0.f);
+    }
+    __syncthreads();
+  }
+}
+// dx[i, j] = g[i] * (exp(x[i, j] - lse[i]) - [j == t_i])
+__global__ void softmax_xent_bw_kernel(float* __restrict__ dx, const float* __restrict__ g, const float* __restrict__ x,
+                                       const float* __restrict__ tgt, const float* __restrict__ lse, long long n, int C) {
+  const long long total = n * C;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = idx / C;
+    const int j = static_cast<int>(idx - i * C);
+    const float p = expf(__ldg(x + idx) - __ldg(lse + i));
+    dx[idx] = __ldg(g + i) * (p - ((static_cast<int>(__ldg(tgt + i)) == j) ? 1.f : 0.f));
+  }
+}
+
 static bool make_layout(Layout* l, const int* shape, const int* strides, int nd) {
   if (nd < 1 || nd > kMaxDims) return false;
   l->nd = nd;
@@ -435,6 +536,51 @@ int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, cons
   st.ob = out_strides[0], st.om = out_strides[1], st.on = out_strides[2];
   dim3 grid((p + 63) / 64, (m + 63) / 64, batch);
   matmul_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, a, b, st, m, p, n);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+
+int fa_embedding_fw_dev(float* out, const float* ids, const float* W, long long n, int V, int E, fa_stream_t stream) {
+  clear_error();
+  if (!out || !ids || !W || n < 0 || V <= 0 || E <= 0) return set_error(FA_ERR_INVALID, "fa_embedding_fw_dev: bad arguments");
+  if (n == 0) return FA_OK;
+  embedding_fw_kernel<<<grid_for(n * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, ids, W, n, V, E);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+int fa_embedding_bw_dev(float* dW, const float* ids, const float* dout, long long n, int V, int E, fa_stream_t stream) {
+  clear_error();
+  if (!dW || !ids || !dout || n < 0 || V <= 0 || E <= 0) return set_error(FA_ERR_INVALID, "fa_embedding_bw_dev: bad arguments");
+  int threads = ((E + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  embedding_bw_kernel<<<V < 148 * 64 ? V : 148 * 64, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dW, ids, dout, n,
+                                                                                                             V, E);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+int fa_softmax_xent_fw_dev(float* loss, float* lse, const float* logits, const float* targets, long long n, int C,
+                           fa_stream_t stream) {
+  clear_error();
+  if (!loss || !lse || !logits || !targets || n < 0 || C <= 0)
+    return set_error(FA_ERR_INVALID, "fa_softmax_xent_fw_dev: bad arguments");
+  if (n == 0) return FA_OK;
+  softmax_xent_fw_kernel<<<n < 148 * 16 ? (int)n : 148 * 16, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      loss, lse, logits, targets, n, C);
+  count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  return FA_OK;
+}
+int fa_softmax_xent_bw_dev(float* dlogits, const float* dloss, const float* logits, const float* targets, const float* lse,
+                           long long n, int C, fa_stream_t stream) {
+  clear_error();
+  if (!dlogits || !dloss || !logits || !targets || !lse || n < 0 || C <= 0)
+    return set_error(FA_ERR_INVALID, "fa_softmax_xent_bw_dev: bad arguments");
+  if (n == 0) return FA_OK;
+  softmax_xent_bw_kernel<<<grid_for(n * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dlogits, dloss, logits,
+                                                                                                   targets, lse, n, C);
   count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;

@@ -341,6 +341,48 @@ class DeviceKernelOps:
                                                 _st(var).ptr, _st(mean).ptr, rows, hidden, None))
         return inp_grad, gamma_grad, beta_grad
 
+    # ---- embedding lookup / softmax cross-entropy without one-hot matmuls --------------------
+    @staticmethod
+    def embedding_fw(ids, weights):
+        """(*,) ids, (V, E) weights -> (*, E): rows of `weights` (== one_hot(ids) @ weights)."""
+        lib = _lib.load("combine")
+        ids, weights = ids.contiguous(), weights.contiguous()
+        V, E = weights.shape
+        out = weights.zeros(tuple(ids.shape) + (E,))
+        _lib.check(lib, lib.fa_embedding_fw_dev(_st(out).ptr, _st(ids).ptr, _st(weights).ptr, _size(ids), V, E, None))
+        return out
+
+    @staticmethod
+    def embedding_bw(ids, out_grad, num_embeddings: int):
+        """Gradient of the table: (V, E), token rows summed per id in ascending token order (deterministic)."""
+        lib = _lib.load("combine")
+        ids, out_grad = ids.contiguous(), out_grad.contiguous()
+        E = out_grad.shape[-1]
+        dW = out_grad.zeros((num_embeddings, E))
+        _lib.check(lib, lib.fa_embedding_bw_dev(_st(dW).ptr, _st(ids).ptr, _st(out_grad).ptr, _size(ids), num_embeddings, E,
+                                                None))
+        return dW
+
+    @staticmethod
+    def softmax_xent_fw(logits, target):
+        """(n, C) logits, (n,) targets -> (loss (n,), lse (n,))."""
+        lib = _lib.load("combine")
+        logits, target = logits.contiguous(), target.contiguous()
+        n, C = logits.shape
+        loss, lse = logits.zeros((n,)), logits.zeros((n,))
+        _lib.check(lib, lib.fa_softmax_xent_fw_dev(_st(loss).ptr, _st(lse).ptr, _st(logits).ptr, _st(target).ptr, n, C, None))
+        return loss, lse
+
+    @staticmethod
+    def softmax_xent_bw(out_grad, logits, target, lse):
+        lib = _lib.load("combine")
+        out_grad, logits, target, lse = (t.contiguous() for t in (out_grad, logits, target, lse))
+        n, C = logits.shape
+        dx = logits.zeros((n, C))
+        _lib.check(lib, lib.fa_softmax_xent_bw_dev(_st(dx).ptr, _st(out_grad).ptr, _st(logits).ptr, _st(target).ptr,
+                                                   _st(lse).ptr, n, C, None))
+        return dx
+
     @staticmethod
     def set_flash_mode(mode: str) -> None:
         assert mode in ("fp32", "bf16")

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .tensor import GELU, HostTensor, TensorBackend, default_backend, one_hot, softmax, tensor_from_numpy
+from .tensor import GELU, EmbeddingLookup, HostTensor, TensorBackend, default_backend, one_hot, softmax, tensor_from_numpy
 
 datatype = np.float32
 
@@ -107,8 +107,11 @@ class MultiHeadAttention(Module):
 
     def create_causal_mask(self, bs, nh, seq_len):
         """(bs, nh, T, T) additive mask, -finfo(f32).max above the diagonal (:63-71)."""
-        mask = -np.finfo(datatype).max * np.triu(np.ones((bs, nh, seq_len, seq_len), dtype=datatype), 1)
-        return tensor_from_numpy(mask, backend=self.backend)
+        key = (bs, nh, seq_len)
+        if getattr(self, "_mask_key", None) != key:     # constant per shape: build (and upload) it once
+            mask = -np.finfo(datatype).max * np.triu(np.ones((bs, nh, seq_len, seq_len), dtype=datatype), 1)
+            self._mask, self._mask_key = tensor_from_numpy(mask, backend=self.backend), key
+        return self._mask
 
     def project_to_query_key_value(self, x: HostTensor):
         """q, k, v: permuted NON-contiguous (B, nh, N, d) views of (B, N, nh, d) storage; kT (B, nh, d, N) (:73-107)."""
@@ -158,8 +161,9 @@ class MultiHeadAttention(Module):
 class Embedding(Module):
     """One-hot @ weights, exactly the reference's formulation (minitorch/modules_basic.py:29-71)."""
 
-    def __init__(self, num_embeddings: int, embedding_dim: int, backend: TensorBackend = None):
+    def __init__(self, num_embeddings: int, embedding_dim: int, backend: TensorBackend = None, fused: bool = False):
         super().__init__()
+        self.fused = fused        # gather kernel instead of one_hot @ weights (same values, SURVEY.md 8(f)-4)
         self.backend = backend
         self.num_embeddings = num_embeddings
         self.embedding_dim = embedding_dim
@@ -168,6 +172,8 @@ class Embedding(Module):
 
     def forward(self, x: HostTensor) -> HostTensor:
         bs, seq_len = x.shape
+        if self.fused and hasattr(x.f, "embedding_fw"):
+            return EmbeddingLookup.apply(x, self.weights.value)
         hot = one_hot(x, self.num_embeddings).view(bs * seq_len, self.num_embeddings)
         return (hot @ self.weights.value).view(bs, seq_len, self.embedding_dim)
 
@@ -251,13 +257,14 @@ class DecoderLM(Module):
 
     def __init__(self, n_vocab: int, n_embd: int, n_head: int, n_positions: int, p_dropout: float = 0.1,
                  ln_eps: float = 1e-5, bias: bool = True, backend: TensorBackend = None,
-                 use_fused_kernel: bool = False, use_flash_attention: bool = False):
+                 use_fused_kernel: bool = False, use_flash_attention: bool = False, use_fused_embedding: bool = False):
         super().__init__()
         self.backend = backend if backend is not None else default_backend()
         self.n_embd = n_embd
         self.n_vocab = n_vocab
-        self.token_embeddings = Embedding(n_vocab, n_embd, self.backend)
-        self.position_embeddings = Embedding(n_vocab, n_embd, self.backend)   # (sic) sized by n_vocab in the reference
+        # use_fused_embedding (an extension, default off): gather kernel instead of the one-hot matmul
+        self.token_embeddings = Embedding(n_vocab, n_embd, self.backend, fused=use_fused_embedding)
+        self.position_embeddings = Embedding(n_vocab, n_embd, self.backend, fused=use_fused_embedding)   # (sic) n_vocab rows
         kw = dict(p_dropout=p_dropout, ln_eps=ln_eps, bias=bias, backend=self.backend,
                   use_fused_kernel=use_fused_kernel, use_flash_attention=use_flash_attention)
         self.t_layer_1 = TransformerLayer(n_embd, n_head, **kw)

@@ -45,6 +45,10 @@ class TensorBackend:
         for name in ("attn_softmax_fw", "attn_softmax_bw", "layernorm_fw", "layernorm_bw", "flash_attention_fw",
                      "flash_attention_bw", "flash_attention_causal_fw", "flash_attention_causal_bw"):
             setattr(self, name, getattr(ops, name))
+        # optional fused lookup / loss ops; callers fall back to the one-hot formulation without them
+        for name in ("embedding_fw", "embedding_bw", "softmax_xent_fw", "softmax_xent_bw"):
+            if hasattr(ops, name):
+                setattr(self, name, getattr(ops, name))
 
 
 class _Data:
@@ -192,7 +196,18 @@ class HostTensor:
     # ---- arithmetic the MultiHeadAttention call site needs (minitorch/tensor.py:196-260), all through
     # combine.so's map / zip / reduce / MatrixMultiply ------------------------------------------------
     def _lift(self, b) -> "HostTensor":
-        return b if isinstance(b, HostTensor) else tensor_from_numpy(np.array([b], dtype=datatype), backend=self.backend)
+        """Python scalar -> (1,) tensor.  Constants are cached per backend (on device storage every new scalar
+        would otherwise be its own H2D copy); they are never written to."""
+        if isinstance(b, HostTensor):
+            return b
+        cache = self.backend.__dict__.setdefault("_scalar_cache", {})
+        key = float(b)
+        t = cache.get(key)
+        if t is None:
+            if len(cache) > 256:
+                cache.clear()
+            t = cache[key] = tensor_from_numpy(np.array([b], dtype=datatype), backend=self.backend)
+        return t
 
     def __matmul__(self, b: "HostTensor") -> "HostTensor":
         return MatMul.apply(self, b)
@@ -494,8 +509,41 @@ def one_hot(x: HostTensor, num_classes: int) -> HostTensor:
     return tensor_from_numpy(hot.reshape(*x.shape, num_classes), backend=x.backend)
 
 
-def softmax_loss(logits: HostTensor, target: HostTensor) -> HostTensor:
-    """Cross entropy with reduction=None (minitorch/nn.py:251-271): (minibatch, C), (minibatch,) -> (minibatch,)."""
+class EmbeddingLookup(Function):
+    """weights[ids] as one gather kernel; same values and gradient as one_hot(ids) @ weights
+    (minitorch/modules_basic.py:55-71) without materialising the (tokens, vocab) matrix."""
+
+    @staticmethod
+    def forward(ctx, ids, weights):
+        ctx.save_for_backward(ids, weights.shape[0])
+        return ids.f.embedding_fw(ids, weights)
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, V = ctx.saved_values
+        return None, g.f.embedding_bw(ids, g, V)
+
+
+class SoftmaxCrossEntropy(Function):
+    """logsumexp(logits) - logits[target] per row in one kernel each way (minitorch/nn.py:251-271 composed)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        loss, lse = logits.f.softmax_xent_fw(logits, target)
+        ctx.save_for_backward(logits, target, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, lse = ctx.saved_values
+        return g.f.softmax_xent_bw(g, logits, target, lse), None
+
+
+def softmax_loss(logits: HostTensor, target: HostTensor, fused: bool = False) -> HostTensor:
+    """Cross entropy with reduction=None (minitorch/nn.py:251-271): (minibatch, C), (minibatch,) -> (minibatch,).
+    `fused=True` uses the single-kernel version when the backend has one."""
+    if fused and hasattr(logits.f, "softmax_xent_fw"):
+        return SoftmaxCrossEntropy.apply(logits, target)
     result = logsumexp(logits, dim=1) - (logits * one_hot(target, logits.shape[1])).sum(dim=1)
     return result.view(logits.shape[0])
 

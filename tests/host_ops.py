@@ -80,3 +80,32 @@ class OracleOps:
         dx, dg, db = R.layernorm_bw(out_grad.to_numpy(), inp.to_numpy(), gamma.to_numpy(), beta.to_numpy(),
                                     var.to_numpy(), mean.to_numpy())
         return _new(inp, dx), _new(inp, np.reshape(dg, (1, -1))), _new(inp, np.reshape(db, (1, -1)))
+
+    # fused lookup / loss ops: numpy restatement of the one-hot formulations they replace
+    @staticmethod
+    def embedding_fw(ids, weights):
+        return _new(weights, weights.to_numpy()[ids.to_numpy().astype(np.int64)])
+
+    @staticmethod
+    def embedding_bw(ids, out_grad, num_embeddings):
+        idx = ids.to_numpy().astype(np.int64).reshape(-1)
+        g = out_grad.to_numpy().astype(np.float64).reshape(idx.size, -1)
+        dW = np.zeros((num_embeddings, g.shape[1]))
+        np.add.at(dW, idx, g)
+        return _new(out_grad, dW)
+
+    @staticmethod
+    def softmax_xent_fw(logits, target):
+        x = logits.to_numpy().astype(np.float64)
+        t = target.to_numpy().astype(np.int64)
+        mx = x.max(axis=1)
+        lse = mx + np.log(np.exp(x - mx[:, None]).sum(axis=1) + C.EPS)      # minitorch's log adds EPS
+        return _new(logits, lse - x[np.arange(len(t)), t]), _new(logits, lse)
+
+    @staticmethod
+    def softmax_xent_bw(out_grad, logits, target, lse):
+        x = logits.to_numpy().astype(np.float64)
+        t = target.to_numpy().astype(np.int64)
+        p = np.exp(x - lse.to_numpy().astype(np.float64)[:, None])
+        p[np.arange(len(t)), t] -= 1.0
+        return _new(logits, out_grad.to_numpy().astype(np.float64)[:, None] * p)

@@ -139,3 +139,67 @@ def test_decoder_lm_golden_device_resident(branch):
         if k.startswith("g:"):
             got = params[k[2:]].value.grad.to_numpy()
             np.testing.assert_allclose(got, z[k], atol=tol * max(1.0, float(np.abs(z[k]).max())), rtol=10 * tol, err_msg=k)
+
+
+# ------------------------------------------------------------------ fused lookup / loss kernels
+@pytest.mark.parametrize("n,V,E", [(1, 7, 5), (77, 13, 64), (4992, 10000, 256), (300, 50, 1030)])
+def test_embedding_gather_equals_one_hot_matmul(n, V, E):
+    rng = np.random.default_rng(n + V)
+    W = rng.standard_normal((V, E)).astype(np.float32)
+    ids = rng.integers(0, V, (n,))
+    dout = rng.standard_normal((n, E)).astype(np.float32)
+    w, x = T(W, requires_grad=True), T(ids)
+    out = fb.EmbeddingLookup.apply(x, w)
+    np.testing.assert_array_equal(out.to_numpy(), W[ids])            # a gather moves bits
+    out.backward(T(dout))
+    want = np.zeros((V, E))
+    np.add.at(want, ids, dout.astype(np.float64))
+    np.testing.assert_allclose(w.grad.to_numpy(), want, atol=1e-5 * max(1.0, float(np.abs(want).max())), rtol=1e-5)
+    g2 = ops.embedding_bw(x, T(dout), V).to_numpy()                  # ascending-token accumulation: deterministic
+    np.testing.assert_array_equal(w.grad.to_numpy(), g2)
+    if n * V <= 10 ** 6:                                             # and the formulation it replaces, on the device
+        hot = fb.one_hot(x, V)
+        np.testing.assert_array_equal(out.to_numpy(), (hot @ T(W)).to_numpy())
+
+
+def test_embedding_out_of_range_id_gives_zero_row():
+    W = np.arange(12, dtype=np.float32).reshape(3, 4)
+    out = ops.embedding_fw(T(np.array([2.0, 5.0, -1.0, 0.0])), T(W)).to_numpy()
+    np.testing.assert_array_equal(out, np.stack([W[2], np.zeros(4), np.zeros(4), W[0]]).astype(np.float32))
+
+
+@pytest.mark.parametrize("n,C", [(1, 1), (5, 3), (257, 1000), (4992, 10000)])
+def test_softmax_cross_entropy_kernel_vs_composed_and_fp64(n, C):
+    rng = np.random.default_rng(C)
+    x = (rng.standard_normal((n, C)) * 3).astype(np.float32)
+    t = rng.integers(0, C, (n,))
+    g = rng.standard_normal((n,)).astype(np.float32)
+    lx = T(x, requires_grad=True)
+    loss = fb.softmax_loss(lx, T(t), fused=True)
+    x64 = x.astype(np.float64)
+    mx = x64.max(axis=1)
+    lse = mx + np.log(np.exp(x64 - mx[:, None]).sum(axis=1) + 1e-6)  # minitorch's log(x + EPS)
+    np.testing.assert_allclose(loss.to_numpy(), lse - x64[np.arange(n), t], atol=2e-5, rtol=1e-5)
+    loss.backward(T(g))
+    p = np.exp(x64 - lse[:, None])
+    p[np.arange(n), t] -= 1.0
+    np.testing.assert_allclose(lx.grad.to_numpy(), g[:, None] * p, atol=2e-6, rtol=1e-4)
+    if n * C <= 10 ** 6:       # the composed formulation (minitorch/nn.py:251-271) through the same device ops
+        cx = T(x, requires_grad=True)
+        closs = fb.softmax_loss(cx, T(t))
+        np.testing.assert_allclose(loss.to_numpy(), closs.to_numpy(), atol=2e-5, rtol=1e-5)
+        closs.backward(T(g))
+        np.testing.assert_allclose(lx.grad.to_numpy(), cx.grad.to_numpy(), atol=5e-6, rtol=1e-4)
+
+
+def test_decoder_lm_golden_with_fused_embedding_and_loss():
+    z = np.load(golden("decoder_small.npz")[0])
+    model, params = load_decoder(z, backend=DEV, use_flash_attention=True, use_fused_embedding=True)
+    logits, total = decoder_loss(model, z, backend=DEV, fused_loss=True)
+    np.testing.assert_allclose(logits.to_numpy(), z["logits"], atol=2e-4, rtol=2e-5)
+    assert abs(float(total.to_numpy().reshape(-1)[0]) - float(z["loss"][0])) < 2e-5
+    total.backward()
+    for k in z.files:
+        if k.startswith("g:"):
+            got = params[k[2:]].value.grad.to_numpy()
+            np.testing.assert_allclose(got, z[k], atol=2e-5 * max(1.0, float(np.abs(z[k]).max())), rtol=2e-4, err_msg=k)

@@ -32,11 +32,11 @@ def load_decoder(z, **flags):
     return model, params
 
 
-def decoder_loss(model, z, backend=BACKEND):
+def decoder_loss(model, z, backend=BACKEND, fused_loss=False):
     mk = lambda a: fb.tensor_from_numpy(np.asarray(a, dtype=np.float32), backend=backend)
     logits = model(mk(z["input_ids"]))
     bs, l, c = logits.shape
-    loss = fb.softmax_loss(logits.view(bs * l, c), mk(z["labels"]).view(bs * l))
+    loss = fb.softmax_loss(logits.view(bs * l, c), mk(z["labels"]).view(bs * l), fused=fused_loss)
     w = mk(z["label_token_weights"]).view(bs * l)
     return logits, (loss * w).sum() / w.sum()
 
@@ -56,6 +56,21 @@ def test_decoder_lm_matches_reference_golden(branch):
             got = params[k[2:]].value.grad.to_numpy()
             np.testing.assert_allclose(got, z[k], atol=tol * max(1.0, float(np.abs(z[k]).max())), rtol=10 * tol,
                                        err_msg=k)
+
+
+def test_decoder_lm_fused_embedding_and_loss_match_reference_golden():
+    """Gather-kernel embeddings + single-kernel cross-entropy in place of the one-hot matmuls:
+    same logits / loss / gradients as the reference's composed run."""
+    z = np.load(golden("decoder_small.npz")[0])
+    model, params = load_decoder(z, use_flash_attention=True, use_fused_embedding=True)
+    logits, total = decoder_loss(model, z, fused_loss=True)
+    np.testing.assert_allclose(logits.to_numpy(), z["logits"], atol=2e-4, rtol=2e-5)
+    assert abs(float(total.to_numpy().reshape(-1)[0]) - float(z["loss"][0])) < 2e-5
+    total.backward()
+    for k in z.files:
+        if k.startswith("g:"):
+            got = params[k[2:]].value.grad.to_numpy()
+            np.testing.assert_allclose(got, z[k], atol=2e-5 * max(1.0, float(np.abs(z[k]).max())), rtol=2e-4, err_msg=k)
 
 
 @pytest.mark.parametrize("branch", ["flash", "fused", "composed"])

@@ -27,17 +27,18 @@ def main():
     w[:, n_pos // 2:] = 1.0
     z = dict(input_ids=ids[:, :-1], labels=ids[:, 1:], label_token_weights=w[:, 1:])
     models = {}
-    for branch in ("flash", "fused", "composed"):
+    branches = ("flash", "fused", "composed") + (("flash+lookup",) if residency == "device" else ())
+    for branch in branches:
         np.random.seed(5)
         models[branch] = fb.DecoderLM(n_vocab=n_vocab, n_embd=n_embd, n_head=n_head, n_positions=n_pos, p_dropout=0.0,
-                                      ln_eps=1e-5, bias=True, backend=backend, use_flash_attention=branch == "flash",
-                                      use_fused_kernel=branch == "fused")
+                                      ln_eps=1e-5, bias=True, backend=backend, use_flash_attention=branch.startswith("flash"),
+                                      use_fused_kernel=branch == "fused", use_fused_embedding=branch == "flash+lookup")
     times = {b: [] for b in models}
     loss = {}
     for rnd in range(4):                      # round 0 = warm-up; branches interleaved so none owns the cold start
         for branch, model in models.items():
             t0 = time.perf_counter()
-            _, total = decoder_loss(model, z, backend=backend)
+            _, total = decoder_loss(model, z, backend=backend, fused_loss=branch == "flash+lookup")
             total.backward()
             if rnd:
                 times[branch].append(time.perf_counter() - t0)
