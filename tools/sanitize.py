@@ -26,3 +26,28 @@ for rows, h in ((33, 64), (5, 2048)):
     ln, var, mean = ops.layernorm_fw(T(a), T(gm), T(bt))
     ops.layernorm_bw(T(a), T(a), T(gm), T(bt), var, mean)
 print("companions ok")
+# legacy host-pointer pipeline (several chunks) and the combine / lookup / loss kernels on device storage
+lib = fb._lib.load("flashattention_kernel")
+lib.fa_set_legacy_chunk_bytes(2 * 100 * 32 * 4)
+for mode in ("fp32", "bf16"):
+    ops.set_flash_mode(mode)
+    d = 32 if mode == "fp32" else 64
+    Q, K, V, dO = (T(rng.standard_normal((2, 5, 100, d)).astype(np.float32)) for _ in range(4))
+    O, m, l = ops.flash_attention_causal_fw(Q, K, V)
+    ops.flash_attention_causal_bw(Q, K, V, O, dO, m, l)
+ops.set_flash_mode("fp32")
+lib.fa_set_legacy_chunk_bytes(0)
+print("legacy pipeline ok")
+DEV = fb.TensorBackend(fb.DeviceKernelOps)
+D = lambda a, g=False: fb.tensor_from_numpy(np.asarray(a, np.float32), backend=DEV, requires_grad=g)
+a, b = D(rng.standard_normal((3, 4, 5)), True), D(rng.standard_normal((1, 5)))
+((a * b).permute(2, 0, 1).contiguous().sum(1) + 1.0).sum().backward()
+w, ids = D(rng.standard_normal((11, 6)), True), D(rng.integers(0, 11, (2, 7)))
+emb = fb.EmbeddingLookup.apply(ids, w)
+logits = D(rng.standard_normal((14, 9)), True)
+loss = fb.softmax_loss(logits, D(rng.integers(0, 9, (14,))), fused=True)
+(loss.sum() + (emb * emb).sum()).backward()
+layer = fb.MultiHeadAttention(64, 2, causal=True, p_dropout=0.0, bias=True, backend=DEV, use_flash_attention=True)
+x = D(rng.standard_normal((2, 33, 64)), True)
+layer(x).sum().backward()
+print("device-resident ops ok", float(np.abs(x.grad.to_numpy()).max()))
