@@ -399,8 +399,7 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
     lib.fa_set_mode(fb._lib.FA_MODE_FP32)
     for p, _ in list(bufs.values()) + list(stats.values()):
         lib.fa_free_host(p)
-    h2d = (3 * n + 7 * n + 2 * r) * 4 + (mask.nbytes * 2 if mask is not None else 0)  # fwd: Q,K,V; bwd: Q,K,V,O,dO (+m,l)
-    h2d = (3 * n + 5 * n + 2 * r) * 4
+    h2d = (3 * n + 5 * n + 2 * r) * 4 + (mask.nbytes * 2 if mask is not None else 0)   # fwd: Q,K,V; bwd: Q,K,V,O,dO,m,l
     d2h = (n + 2 * r + 3 * n) * 4
     return {"value": total / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": dt / steps * 1e3, "batch_per_gpu": B,
