@@ -179,3 +179,44 @@ def test_bf16_lazy_rescale_divergent_rows(causal, d):
     for got, want, bnd, name in zip((gq, gk, gv), ge, bounds, ("dQ", "dK", "dV")):
         err = np.abs(got.to_numpy().astype(np.float64) - want)
         assert np.all(err <= TOL + BF16_EPS * np.abs(want) + bnd), (name, float(err.max()))
+
+
+@pytest.mark.timeout(600)
+def test_bf16_full_cfg4_size_properties():
+    """BASELINE config #4 at its full size (B=8, 32 heads, N=4096, d=128, key padding kv_len in [N/2, N]) on the
+    tensor-core path.  A full fp64 oracle would take minutes, so: sampled query rows against the oracle (O, LSE,
+    dQ depend on their own row only), exact zeros for padded keys, and identities that involve every element of
+    dV / dQ / dK:  sum_k dV[k,:] = sum_q dO[q,:]  and  sum dQ*Q = sum dK*K  per (batch, head)."""
+    B, H, N, d = 8, 32, 4096, 128
+    rng = np.random.default_rng(44)
+    kv = rng.integers(N // 2, N + 1, B).astype(np.int32)
+    Q, K, V, dO = (R.round_bf16(rng.standard_normal((B, H, N, d), dtype=np.float32)) for _ in range(4))
+    dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(x, "bf16") for x in (Q, K, V, dO))
+    dkv = dev.DeviceArray.from_numpy(kv)
+    O, m, l = dev.flash_fwd(dq, dk, dv, kv_len=dkv)
+    gq, gk, gv = dev.flash_bwd(dq, dk, dv, O, ddo, m, l, kv_len=dkv)
+    O, m, l, gq, gk, gv = (t.to_numpy() for t in (O, m, l, gq, gk, gv))
+    sc = 1.0 / np.sqrt(d)
+    rows = np.unique(np.concatenate([[0, 127, 128, N - 1], rng.integers(0, N, 12)]))
+    for b, h in ((0, 0), (3, 17), (B - 1, H - 1)):
+        n = int(kv[b])
+        q64, k64, v64, do64 = (x[b, h].astype(np.float64) for x in (Q, K, V, dO))
+        S = (q64[rows] @ k64[:n].T) * sc
+        mx = S.max(axis=1, keepdims=True)
+        P = np.exp(S - mx)
+        lsum = P.sum(axis=1, keepdims=True)
+        P /= lsum
+        Oe = P @ v64[:n]
+        assert np.abs(O[b, h, rows] - Oe).max() < TOL
+        assert np.abs(m[b, h, rows] + np.log(l[b, h, rows]) - (mx + np.log(lsum))[:, 0]).max() < 2e-3
+        dS = P * (do64[rows] @ v64[:n].T - (do64[rows] * Oe).sum(axis=1, keepdims=True))
+        dQe = (dS @ k64[:n]) * sc
+        assert np.all(np.abs(gq[b, h, rows] - dQe) <= TOL + BF16_EPS * np.abs(dQe))
+        assert not gk[b, :, n:].any() and not gv[b, :, n:].any()          # padded keys: exactly zero gradients
+    f64 = lambda x: x.astype(np.float64)
+    sum_dv, sum_do = f64(gv).sum(axis=2), f64(dO).sum(axis=2)
+    bound = BF16_EPS * (np.abs(f64(gv)).sum(axis=2) + np.abs(f64(dO)).sum(axis=2))
+    assert np.all(np.abs(sum_dv - sum_do) <= bound)
+    lhs, rhs = (f64(gq) * f64(Q)).sum(axis=(2, 3)), (f64(gk) * f64(K)).sum(axis=(2, 3))
+    scale_ = np.abs(f64(gq) * f64(Q)).sum(axis=(2, 3)) + np.abs(f64(gk) * f64(K)).sum(axis=(2, 3))
+    assert np.all(np.abs(lhs - rhs) <= 2 * BF16_EPS * scale_)
