@@ -18,9 +18,9 @@ from .tensor import (Attn_Softmax, EmbeddingLookup, SoftmaxCrossEntropy, FlashAt
                      tensor_from_numpy)
 from . import modules_transformer
 from .modules_transformer import (DecoderLM, Dropout, Embedding, FeedForward, FusedLayerNorm, LayerNorm1d, Linear,
-                                  MultiHeadAttention, TransformerLayer)
+                                  MultiHeadAttention, TransformerLayer, generate)
 
 __all__ = ["CudaKernelOps", "DeviceKernelOps", "DeviceStorage", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
            "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding", "softmax", "modules_transformer",
            "MultiHeadAttention", "Linear", "Dropout", "DecoderLM", "TransformerLayer", "FeedForward", "Embedding",
-           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU", "EmbeddingLookup", "SoftmaxCrossEntropy"]
+           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU", "EmbeddingLookup", "SoftmaxCrossEntropy", "generate"]

@@ -284,3 +284,21 @@ class DecoderLM(Module):
             x = layer(x)
         x = self.ln(x.contiguous().view(batch_size * seq_len, self.n_embd))
         return self.lm_head(x).view(batch_size, seq_len, self.n_vocab)
+
+
+def generate(model: DecoderLM, token_ids, model_max_length: int, eos_id: int = -1):
+    """Greedy decoding exactly as the reference does it (project/run_machine_translation.py:300-325): the model is
+    re-run on the WHOLE prefix for every new token (no KV cache) and the arg-max of the last position is appended,
+    until `eos_id` or `model_max_length` tokens.  Returns the full id list.  Attention here is the decode regime of
+    SURVEY.md 8(f)-3 (batch 1, N <= model_max_length): launch-latency bound, so what matters is that nothing
+    crosses PCIe per op -- use a device-resident backend."""
+    model.eval()
+    ids = [int(t) for t in token_ids]
+    while len(ids) <= model_max_length:
+        x = tensor_from_numpy(np.asarray(ids, dtype=datatype).reshape(1, len(ids)), backend=model.backend)
+        logits = model(x)
+        gen_id = int(np.argmax(logits.to_numpy()[0, len(ids) - 1, :]))
+        if gen_id == eos_id:
+            break
+        ids.append(gen_id)
+    return ids

@@ -117,3 +117,17 @@ def test_autograd_nodes_against_finite_differences():
             args_lo = [lo if a is arr else a for a in (x0, W0, b0)]
             fd = (float(f(*args_hi)[0].to_numpy().reshape(-1)[0]) - float(f(*args_lo)[0].to_numpy().reshape(-1)[0])) / (2 * e)
             assert abs(fd - g[idx]) < 5e-3 * max(1.0, abs(fd)), (idx, fd, g[idx])
+
+
+def test_generate_greedy_matches_stepwise_argmax_and_is_branch_independent():
+    """generate() (project/run_machine_translation.py:300-325): flash and composed models with the same weights
+    emit the same tokens, and each token is the arg-max of a fresh full-prefix forward."""
+    z = np.load(golden("decoder_small.npz")[0])
+    flash, _ = load_decoder(z, use_flash_attention=True)
+    comp, _ = load_decoder(z)
+    prompt = [int(t) for t in z["input_ids"][0, :5]]
+    a = fb.generate(flash, prompt, model_max_length=12)
+    b = fb.generate(comp, prompt, model_max_length=12)
+    assert a == b and a[:5] == prompt and len(a) == 13
+    logits = flash(T(np.asarray(a[:-1], dtype=np.float32).reshape(1, -1))).to_numpy()
+    assert int(np.argmax(logits[0, -1])) == a[-1]
