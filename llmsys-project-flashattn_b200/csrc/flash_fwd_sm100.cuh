@@ -88,8 +88,10 @@ __device__ __forceinline__ void pin16(const uint32_t (&r)[16], float f) {
 }
 
 #ifndef FA_FWD_EMU
-#define FA_FWD_EMU 0   // exponentials per 8 evaluated on the FMA pipe instead of MUFU (measured on B200:
-                       // 0 -> 1.53 ms, 2 -> 1.62 ms, 3 -> 1.75 ms at cfg4: the FP32 pipe is the busier one, so off)
+#define FA_FWD_EMU 1   // column PAIRS of every 8 scores whose exponentials are evaluated by the packed polynomial on the
+                       // FMA pipe (ex2_poly2) instead of MUFU.EX2.  Interleaved in-process A/B on B200 at cfg4, sustained
+                       // (power-capped) clocks, tools/ab_kernels.py: 0 -> 1.496 ms, 1 -> 1.39-1.40 ms, 2 -> 1.56 ms.
+                       // (An earlier scalar variant, 9 issue slots per exponential, was slower at every setting.)
 #endif
 // MASKMODE: 0 none (N-ragged only), 1 kv_len[b], 2 additive key mask (B,N)
 template <int D, bool CAUSAL, int MASKMODE, typename OutT>
@@ -354,10 +356,21 @@ __global__ void __launch_bounds__(640, 1)
           for (int t = 0; t < 8; t += 2) {
             float x0, x1;
             f32x2_unpack(fma_f32x2(f32x2(s[i + t], s[i + t + 1]), sc2, nm2), x0, x1);
-            const bool emu0 = (EMU >= 2 && t == 2) || (EMU >= 4 && t == 6);
-            const bool emu1 = (EMU >= 1 && t == 6) || (EMU >= 3 && t == 4);
-            e[t] = emu0 ? ex2_poly(x0) : ex2_approx(x0);
-            e[t + 1] = emu1 ? ex2_poly(x1) : ex2_approx(x1);
+            // EMU of the four column PAIRS of every 8 go to the packed polynomial (FMA pipe), the rest to MUFU.EX2
+#ifndef FA_FWD_EMU_POS
+#define FA_FWD_EMU_POS 6
+#endif
+#ifndef FA_FWD_EMU_EVERY
+#define FA_FWD_EMU_EVERY 8
+#endif
+            const bool emu = ((EMU >= 1 && t == FA_FWD_EMU_POS) || (EMU >= 2 && t == 2) || (EMU >= 3 && t == 4) ||
+                              (EMU >= 4 && t == 0)) && (i % FA_FWD_EMU_EVERY == 0);
+            if (emu) {
+              ex2_poly2(x0, x1, e[t], e[t + 1]);
+            } else {
+              e[t] = ex2_approx(x0);
+              e[t + 1] = ex2_approx(x1);
+            }
           }
           ra = add_f32x2(ra, add_f32x2(f32x2(e[0], e[1]), f32x2(e[4], e[5])));
           rb = add_f32x2(rb, add_f32x2(f32x2(e[2], e[3]), f32x2(e[6], e[7])));

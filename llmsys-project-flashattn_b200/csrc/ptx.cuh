@@ -328,6 +328,24 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// ex2_poly for two values at once: the range reduction and the Horner steps are packed (FADD2 / FFMA2), so a pair
+// costs 2 FMNMX + 3 FADD2/FFMA2 (reduction) + 3 FFMA2 (polynomial) + 2 integer shift-adds = 10 issue slots.
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& e0, float& e1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t x = f32x2(x0, x1);
+  const uint64_t t = add_f32x2(x, f32x2(12582912.0f, 12582912.0f));
+  const uint64_t r = add_f32x2(t, f32x2(-12582912.0f, -12582912.0f));          // round(x)
+  const uint64_t f = fma_f32x2(r, f32x2(-1.0f, -1.0f), x);                       // x - round(x) in [-0.5, 0.5]
+  uint64_t pl = fma_f32x2(f32x2(0.0551716685f, 0.0551716685f), f, f32x2(0.2426111251f, 0.2426111251f));
+  pl = fma_f32x2(pl, f, f32x2(0.6932609677f, 0.6932609677f));
+  pl = fma_f32x2(pl, f, f32x2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1;
+  f32x2_unpack(pl, p0, p1);
+  f32x2_unpack(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
