@@ -357,14 +357,11 @@ __global__ void __launch_bounds__(640, 1)
             float x0, x1;
             f32x2_unpack(fma_f32x2(f32x2(s[i + t], s[i + t + 1]), sc2, nm2), x0, x1);
             // EMU of the four column PAIRS of every 8 go to the packed polynomial (FMA pipe), the rest to MUFU.EX2
-#ifndef FA_FWD_EMU_POS
-#define FA_FWD_EMU_POS 6
+#ifdef FA_FWD_EMU_MASK     // experiment: bit k set = column pair k of the 16 pairs of a 32-score chunk uses the polynomial
+            const bool emu = ((FA_FWD_EMU_MASK >> ((i + t) / 2)) & 1) != 0;
+#else
+            const bool emu = (EMU >= 1 && t == 6) || (EMU >= 2 && t == 2) || (EMU >= 3 && t == 4) || (EMU >= 4 && t == 0);
 #endif
-#ifndef FA_FWD_EMU_EVERY
-#define FA_FWD_EMU_EVERY 8
-#endif
-            const bool emu = ((EMU >= 1 && t == FA_FWD_EMU_POS) || (EMU >= 2 && t == 2) || (EMU >= 3 && t == 4) ||
-                              (EMU >= 4 && t == 0)) && (i % FA_FWD_EMU_EVERY == 0);
             if (emu) {
               ex2_poly2(x0, x1, e[t], e[t + 1]);
             } else {
