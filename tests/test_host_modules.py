@@ -131,3 +131,53 @@ def test_generate_greedy_matches_stepwise_argmax_and_is_branch_independent():
     assert a == b and a[:5] == prompt and len(a) == 13
     logits = flash(T(np.asarray(a[:-1], dtype=np.float32).reshape(1, -1))).to_numpy()
     assert int(np.argmax(logits[0, -1])) == a[-1]
+
+
+def test_module_tree_train_eval_and_dropout():
+    """Module.train()/eval() reach every sub-module; Dropout is the identity at p = 0 or in eval mode and rescales
+    by 1/(1-p) in training (minitorch/modules_basic.py:73-101)."""
+    np.random.seed(0)
+    layer = fb.TransformerLayer(16, 2, p_dropout=0.5, backend=BACKEND, use_flash_attention=True)
+    layer.eval()
+    assert not layer.attention.dropout.training and not layer.ff.dropout.training
+    layer.train()
+    assert layer.attention.dropout.training and layer.ff.training
+    x = T(np.ones((4, 8)))
+    d = fb.Dropout(0.5)
+    d.eval()
+    assert d(x) is x
+    d.train()
+    y = d(x).to_numpy()
+    assert set(np.unique(y)) <= {0.0, 2.0} and 0 < (y == 0).sum() < y.size
+    assert fb.Dropout(0.0)(x) is x
+
+
+def test_linear_init_and_parameter_names():
+    np.random.seed(1)
+    lin = fb.Linear(64, 32, True, BACKEND)
+    w = lin.weights.value.to_numpy()
+    assert w.shape == (64, 32) and np.abs(w).max() <= (1 / 64) ** 0.5 + 1e-7       # uniform(+-1/sqrt(in))
+    names = [n for n, _ in fb.DecoderLM(11, 16, 2, 8, backend=BACKEND).named_parameters()]
+    assert "t_layer_3.attention.k_projection.bias" in names and "lm_head.weights" in names and len(names) == 70
+    y = lin(T(np.ones((3, 64))))
+    np.testing.assert_allclose(y.to_numpy(), np.ones((3, 64)) @ w + lin.bias.value.to_numpy(), atol=1e-5)
+
+
+def test_transformer_layer_flash_equals_composed_and_fused():
+    """Pre-LN block (minitorch/modules_transfomer.py:278-336): same weights through the three attention cores."""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 10, 32)).astype(np.float32)
+    g = rng.standard_normal((2, 10, 32)).astype(np.float32)
+    np.random.seed(3)
+    ref = fb.TransformerLayer(32, 4, p_dropout=0.0, ln_eps=1e-5, backend=BACKEND)
+    outs = []
+    for flags in ({}, {"use_flash_attention": True}):
+        np.random.seed(3)
+        layer = fb.TransformerLayer(32, 4, p_dropout=0.0, ln_eps=1e-5, backend=BACKEND, **flags)
+        X = T(x, True)
+        Y = layer(X)
+        Y.backward(T(g))
+        outs.append((Y.to_numpy(), X.grad.to_numpy(), layer.ff.linear_in.weights.value.grad.to_numpy()))
+    for a, b in zip(*outs):
+        np.testing.assert_allclose(a, b, atol=2e-5 * max(1.0, float(np.abs(b).max())), rtol=1e-5)
+    assert ref is not None
