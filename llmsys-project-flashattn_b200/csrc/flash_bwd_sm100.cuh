@@ -216,14 +216,6 @@ __global__ void __launch_bounds__(640, 1)
   const int nq = (p.N + 127) >> 7;
   const int q_first = CAUSAL ? kt : 0;
   const int n_iter = nq - q_first;
-#ifdef FA_BWD_ROT
-  // non-causal: the 32 KV-tile CTAs of a head would all reduce into dQ tile i at about the same time (same sweep
-  // order); start each CTA's sweep at a different Q tile so the L2 add-reductions spread over different lines
-  const int rot = CAUSAL ? 0 : (kt % nq);
-#define FA_QTILE(it) (q_first + (((it) + rot) % n_iter))
-#else
-#define FA_QTILE(it) (q_first + (it))
-#endif
   __nv_bfloat16* dKb = reinterpret_cast<__nv_bfloat16*>(p.dK) + b * p.sb + h * p.sh;
   __nv_bfloat16* dVb = reinterpret_cast<__nv_bfloat16*>(p.dV) + b * p.sb + h * p.sh;
 
@@ -286,7 +278,7 @@ __global__ void __launch_bounds__(640, 1)
         const long long vec_base = (static_cast<long long>(b) * p.H + h) * p.Npad;
         for (int it = 0; it < n_iter; ++it) {
           const int s = it & 1;
-          const int q0 = FA_QTILE(it) * 128;
+          const int q0 = (q_first + it) * 128;
           mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1);
           mbar_expect_tx(&q_full[s], Cfg::TILE_BYTES + 1024);
 #pragma unroll
@@ -412,7 +404,7 @@ __global__ void __launch_bounds__(640, 1)
         constexpr int PER_WG = D / 64;   // 32-column boxes per warpgroup and iteration
         const int hh = warp - 18;
         for (int it = 0; it < n_iter; ++it) {
-          const int q0 = FA_QTILE(it) * 128;
+          const int q0 = (q_first + it) * 128;
           for (int c2 = 0; c2 < PER_WG; ++c2) {
             mbar_wait(&stg_full[hh], (it * PER_WG + c2) & 1);
             tma_reduce_add_4d(&tmdQ, sStg + hh * Cfg::STG_BYTES, (D / 2) * hh + 32 * c2, q0, h, b);
@@ -449,7 +441,7 @@ __global__ void __launch_bounds__(640, 1)
 
     for (int it = g; it < n_iter; it += 2) {
       const int ph = (it >> 1) & 1;
-      const int q0 = FA_QTILE(it) * 128;
+      const int q0 = (q_first + it) * 128;
       const float* nlse = sVec + g * 256 + 64 * hh;   // -LSE2 of my 64 queries
       const float* dv = sVec + g * 256 + 128 + 64 * hh;
       // ---- P^T = exp2(S^T * scale*log2e - LSE2[q])
