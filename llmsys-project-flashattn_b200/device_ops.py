@@ -70,7 +70,7 @@ def _st(t) -> DeviceStorage:
 
 def _layout(t):
     d = t._tensor
-    return _i32(d.shape), _i32(d.strides)
+    return d._shape, d._strides        # cached int32 arrays (tensor.py::_Data)
 
 
 def _size(t) -> int:

@@ -66,12 +66,18 @@ class _Data:
         self.strides = tuple(int(s) for s in strides)
 
     @property
-    def _shape(self) -> np.ndarray:      # minitorch.TensorData attribute names
-        return np.array(self.shape, dtype=np.int32)
+    def _shape(self) -> np.ndarray:      # minitorch.TensorData attribute names; built once (read-only by convention)
+        a = self.__dict__.get("_shape_i32")
+        if a is None:
+            a = self.__dict__["_shape_i32"] = np.ascontiguousarray(np.array(self.shape, dtype=np.int32).reshape(-1))
+        return a
 
     @property
     def _strides(self) -> np.ndarray:
-        return np.array(self.strides, dtype=np.int32)
+        a = self.__dict__.get("_strides_i32")
+        if a is None:
+            a = self.__dict__["_strides_i32"] = np.ascontiguousarray(np.array(self.strides, dtype=np.int32).reshape(-1))
+        return a
 
     def is_contiguous(self) -> bool:
         exp = 1
