@@ -277,6 +277,81 @@ __global__ void softmax_xent_bw_kernel(float* __restrict__ dx, const float* __re
   }
 }
 
+
+// Large-problem variant: 128x128 output tile, 8x8 register micro-tile per thread (256 threads), K step 16, the next
+// K slab prefetched into registers while the current one is multiplied out of shared memory.  Same arbitrary-stride
+// operand addressing as matmul_kernel; used when both M and N reach 128 (Linear / embedding / lm_head matmuls).
+__global__ void __launch_bounds__(256) matmul128_kernel(float* __restrict__ out, const float* __restrict__ A,
+                                                        const float* __restrict__ Bm, MMStrides st, int M, int N, int K) {
+  __shared__ __align__(16) float As[16][128 + 4];   // [k][m]
+  __shared__ __align__(16) float Bs[16][128 + 4];   // [k][n]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128, b = blockIdx.z;
+  const float* Ab = A + b * st.ab;
+  const float* Bb = Bm + b * st.bb;
+  // loader mapping: A slab 128(m) x 16(k): thread -> k = tid & 15, m = (tid >> 4) + 16 * t  (t = 0..7)
+  //                 B slab 16(k) x 128(n): thread -> n = tid & 127, k = (tid >> 7) + 2 * t
+  const int a_k = threadIdx.x & 15, a_m = threadIdx.x >> 4;
+  const int b_n = threadIdx.x & 127, b_k = threadIdx.x >> 7;
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int gm = m0 + a_m + 16 * t, gk = k0 + a_k;
+      ra[t] = (gm < M && gk < K) ? __ldg(Ab + gm * st.am + gk * st.ak) : 0.f;
+      const int gn = n0 + b_n, gk2 = k0 + b_k + 2 * t;
+      rb[t] = (gn < N && gk2 < K) ? __ldg(Bb + gk2 * st.bk + gn * st.bn) : 0.f;
+    }
+  };
+  float acc[8][8] = {};
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      As[a_k][a_m + 16 * t] = ra[t];
+      Bs[b_k + 2 * t][b_n] = rb[t];
+    }
+    __syncthreads();
+    if (k0 + 16 < K) fetch(k0 + 16);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Ob = out + b * st.ob;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn < N) Ob[gm * st.om + gn * st.on] = acc[i][j];
+    }
+  }
+}
+
+static void launch_matmul(float* out, const float* a, const float* b, const MMStrides& st, int batch, int m, int p, int n,
+                          cudaStream_t stream) {
+  if (m >= 128 && p >= 128) {
+    dim3 grid((p + 127) / 128, (m + 127) / 128, batch);
+    matmul128_kernel<<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n);
+  } else {
+    dim3 grid((p + 63) / 64, (m + 63) / 64, batch);
+    matmul_kernel<<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n);
+  }
+}
+
 static bool make_layout(Layout* l, const int* shape, const int* strides, int nd) {
   if (nd < 1 || nd > kMaxDims) return false;
   l->nd = nd;
@@ -439,8 +514,7 @@ void MatrixMultiply(float* out, int* out_shape, int* out_strides, float* a_stora
   st.bb = (b_shape[0] > 1) ? b_strides[0] : 0;
   st.bk = b_strides[1], st.bn = b_strides[2];
   st.ob = out_strides[0], st.om = out_strides[1], st.on = out_strides[2];
-  dim3 grid((p + 63) / 64, (m + 63) / 64, batch);
-  matmul_kernel<<<grid, 256>>>(d_out, d_a, d_b, st, m, p, n);
+  launch_matmul(d_out, d_a, d_b, st, batch, m, p, n, 0);
   count_launch();
   CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * eo, cudaMemcpyDeviceToHost, 0));
@@ -534,8 +608,7 @@ int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, cons
   st.bb = (b_shape[0] > 1) ? b_strides[0] : 0;
   st.bk = b_strides[1], st.bn = b_strides[2];
   st.ob = out_strides[0], st.om = out_strides[1], st.on = out_strides[2];
-  dim3 grid((p + 63) / 64, (m + 63) / 64, batch);
-  matmul_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, a, b, st, m, p, n);
+  launch_matmul(out, a, b, st, batch, m, p, n, reinterpret_cast<cudaStream_t>(stream));
   count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;

@@ -133,3 +133,21 @@ def test_errors_are_reported_not_fatal():
         ops.map("sqrt")
     with pytest.raises(fb.FlashAttnError):
         ops.map("neg")(T(np.zeros((1,) * 9, np.float32)))     # > 8 dims
+
+
+@pytest.mark.parametrize("B,M,K,N", [(1, 128, 16, 128), (2, 200, 77, 150), (1, 129, 300, 385), (3, 256, 5, 128)])
+def test_matmul_large_tile_kernel_vs_oracle(B, M, K, N):
+    """M, N >= 128 take the 128x128 register-blocked kernel: ragged edges, K not a multiple of the K step,
+    transposed (permuted) operands and a broadcast 2-D right operand -- host- and device-pointer entry points."""
+    rng = np.random.default_rng(B * 1000 + M + K + N)
+    a = rng.standard_normal((B, M, K)).astype(np.float32)
+    b = rng.standard_normal((B, K, N)).astype(np.float32)
+    w = rng.standard_normal((K, N)).astype(np.float32)
+    at = np.ascontiguousarray(a.transpose(0, 2, 1))         # stored (B, K, M), used as its transpose
+    tol = dict(atol=1e-5 * K + 2e-5, rtol=1e-5)
+    want, want_w = C.matrix_multiply(a, b), C.matrix_multiply(a, w)
+    DEV = fb.TensorBackend(fb.DeviceKernelOps)
+    for o, mk in ((ops, T), (fb.DeviceKernelOps, lambda x: fb.tensor_from_numpy(x, backend=DEV))):
+        close(o.matrix_multiply(mk(a), mk(b)).to_numpy(), want, **tol)
+        close(o.matrix_multiply(mk(a), mk(w)).to_numpy(), want_w, **tol)
+        close(o.matrix_multiply(mk(at).permute(0, 2, 1), mk(b)).to_numpy(), want, **tol)
