@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(640, 1)
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<D>;
   constexpr int NSTAGE = Cfg::NSTAGE;
-  constexpr int EMU = FA_FWD_EMU;
+#ifndef FA_FWD_EMU_D64
+#define FA_FWD_EMU_D64 FA_FWD_EMU
+#endif
+  constexpr int EMU = (D == 64) ? FA_FWD_EMU_D64 : FA_FWD_EMU;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align by offset (not by pointer cast) so the compiler keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

@@ -21,7 +21,8 @@ for d in dirs:
             getattr(lib, sym).restype, getattr(lib, sym).argtypes = restype, argtypes
     libs.append(lib)
 L0 = libs[0]
-B, H, N, d = 8, 32, 4096, 128
+d = int(os.environ.get("AB_D", "128"))
+B, H, N = 8, 32, 4096
 n = B * H * N * d
 rng = np.random.default_rng(0)
 kv = rng.integers(N // 2, N + 1, B).astype(np.int32)
