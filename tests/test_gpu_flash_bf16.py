@@ -220,3 +220,30 @@ def test_bf16_full_cfg4_size_properties():
     lhs, rhs = (f64(gq) * f64(Q)).sum(axis=(2, 3)), (f64(gk) * f64(K)).sum(axis=(2, 3))
     scale_ = np.abs(f64(gq) * f64(Q)).sum(axis=(2, 3)) + np.abs(f64(gk) * f64(K)).sum(axis=(2, 3))
     assert np.all(np.abs(lhs - rhs) <= 2 * BF16_EPS * scale_)
+
+
+@pytest.mark.parametrize("dtype,d", [("bf16", 128), ("bf16", 64), ("f32", 32)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_fully_padded_batch_gives_exact_zeros(dtype, d, causal):
+    """kv_len[b] = 0 (a batch with no valid key at all): O, dQ, dK, dV of that batch are exactly zero, m = -inf,
+    l = 0, nothing is NaN, and the other batch is unaffected."""
+    B, H, N = 2, 2, 300
+    rng = np.random.default_rng(3)
+    Q, K, V, dO = (R.round_bf16(rng.standard_normal((B, H, N, d)).astype(np.float32)) for _ in range(4))
+    kv = np.array([0, 200], dtype=np.int32)
+    dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(x, dtype) for x in (Q, K, V, dO))
+    dkv = dev.DeviceArray.from_numpy(kv)
+    O, m, l = dev.flash_fwd(dq, dk, dv, causal=causal, kv_len=dkv)
+    gq, gk, gv = dev.flash_bwd(dq, dk, dv, O, ddo, m, l, causal=causal, kv_len=dkv)
+    O, m, l, gq, gk, gv = (t.to_numpy() for t in (O, m, l, gq, gk, gv))
+    for name, x in (("O", O), ("dQ", gq), ("dK", gk), ("dV", gv)):
+        assert not np.isnan(x).any(), name
+        assert not x[0].any(), name
+    assert np.all(np.isneginf(m[0])) and not l[0].any()
+    Oe, _, _ = R.attention_fwd(Q[1:], K[1:], V[1:], causal=causal, kv_len=kv[1:])
+    ge = R.attention_bwd(Q[1:], K[1:], V[1:], dO[1:], causal=causal, kv_len=kv[1:])
+    tol = TOL if dtype == "bf16" else 1e-5
+    assert maxabs(O[1:], Oe) < tol
+    for got, want in zip((gq, gk, gv), ge):
+        ok, err = close_bf16(got[1:], want) if dtype == "bf16" else (maxabs(got[1:], want) < 1e-5 * max(1.0, float(np.abs(want).max())), 0)
+        assert ok, err
