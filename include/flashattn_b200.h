@@ -28,12 +28,12 @@ extern "C" {
 
 typedef struct CUstream_st* fa_stream_t; /* == cudaStream_t; NULL = default stream */
 
-/* ---- status (all three libraries) ------------------------------------------------- */
+/* ---- status (all four libraries) ------------------------------------------------- */
 enum { FA_OK = 0, FA_ERR_INVALID = 1, FA_ERR_UNSUPPORTED = 2, FA_ERR_CUDA = 3 };
 int fa_last_status(void);          /* status of the most recent call into this library */
 const char* fa_last_error(void);   /* human-readable message for it ("" when FA_OK)     */
 
-/* ---- device-memory / timing utilities (all three libraries) ----------------------- */
+/* ---- device-memory / timing utilities (all four libraries) ----------------------- */
 int fa_device_count(void);
 int fa_set_device(int dev);
 void* fa_malloc(size_t bytes);                 /* NULL on failure */

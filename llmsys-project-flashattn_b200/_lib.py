@@ -37,7 +37,7 @@ class fa_attn_desc(ctypes.Structure):
 
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, ndim=1, flags="C_CONTIGUOUS")
 
-# symbol -> (restype, argtypes); shared by all three libraries
+# symbol -> (restype, argtypes); shared by all four libraries
 _COMMON = {
     "fa_last_status": (c_int, []),
     "fa_last_error": (c_char_p, []),

@@ -1,4 +1,4 @@
-// Host-side plumbing shared by the three shared libraries (included once per .so):
+// Host-side plumbing shared by the four shared libraries (included once per .so):
 // status/error reporting, a grow-only device scratch pool for the legacy host-pointer
 // entry points (the reference does cudaMalloc/cudaFree on every call,
 // src/flashattention_kernel.cu:280-324), and the fa_* utility exports declared in
