@@ -134,3 +134,68 @@ def test_autograd_nodes_softmax_layernorm():
     assert maxabs(at.grad.to_numpy(), dxe) < 1e-4
     assert maxabs(gt.grad.to_numpy(), dge.reshape(-1)) < 1e-4
     assert maxabs(bt.grad.to_numpy(), dbe.reshape(-1)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's kernel_tests, run live: random shapes drawn like its TestDecorator (kernel_tests/test_utils.py:
+# batch * seq <= 1024, seq <= 512, nhead 8, hidden 32; 5 draws), the fused op against the COMPOSED minitorch-style ops
+# on the same backend, with the reference's own tolerances.
+# ------------------------------------------------------------------------------------------------------------------
+def _bs_sl(rng):
+    seq = int(rng.integers(1, 513))
+    return int(rng.integers(1, max(2, 1024 // seq + 1))), seq
+
+
+@pytest.mark.parametrize("draw", range(5))
+@pytest.mark.parametrize("storage", ["host", "device"])
+def test_kernel_tests_softmax_recipe_live(draw, storage):
+    """kernel_tests/test_softmax_fw.py:60-72 (softmax(inp + mask) baseline, 1e-3) and test_softmax_bw.py:48-52
+    (soft * (grad - sum(grad * soft)), atol 1e-2 rtol 1e-3)."""
+    backend = fb.TensorBackend(fb.DeviceKernelOps if storage == "device" else fb.CudaKernelOps)
+    mk = lambda a, g=False: fb.tensor_from_numpy(np.asarray(a, np.float32), backend=backend, requires_grad=g)
+    rng = np.random.default_rng(100 + draw)
+    B, to_len = _bs_sl(rng)
+    from_len, nhead = to_len, 8
+    if B * nhead * from_len * to_len > 2 ** 24:
+        from_len = max(1, 2 ** 24 // (B * nhead * to_len))
+    inp = rng.uniform(-1, 1, (B, nhead, from_len, to_len)).astype(np.float32)
+    valid = rng.integers(1, to_len + 1, B)
+    mask = np.where(np.arange(to_len)[None, :] < valid[:, None], 0.0, -1e8).astype(np.float32)
+    cust = mk(inp.copy()).attn_softmax(mk(mask.reshape(B, 1, 1, to_len)))
+    base = fb.softmax(mk(inp) + mk(mask.reshape(B, 1, 1, to_len)), dim=3)
+    np.testing.assert_allclose(cust.to_numpy(), base.to_numpy(), atol=1e-3, rtol=1e-3)
+    grad = rng.uniform(-1, 1, inp.shape).astype(np.float32)
+    soft = base.to_numpy()
+    x = mk(inp.copy(), True)
+    x.attn_softmax(mk(mask.reshape(B, 1, 1, to_len))).backward(mk(grad))
+    want = soft * (grad - (grad * soft).sum(axis=3, keepdims=True))
+    np.testing.assert_allclose(x.grad.to_numpy(), want, atol=1e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("draw", range(5))
+@pytest.mark.parametrize("storage", ["host", "device"])
+def test_kernel_tests_layernorm_recipe_live(draw, storage):
+    """kernel_tests/test_layernorm_fw.py:50-69 (atol 1e-2 rtol 1e-3) and test_layernorm_bw.py:136-161
+    (atol 1e-3 rtol 1e-2): composed mean / var / normalise / affine on the same backend as the baseline."""
+    backend = fb.TensorBackend(fb.DeviceKernelOps if storage == "device" else fb.CudaKernelOps)
+    mk = lambda a, g=False: fb.tensor_from_numpy(np.asarray(a, np.float32), backend=backend, requires_grad=g)
+    rng = np.random.default_rng(200 + draw)
+    b, s = _bs_sl(rng)
+    rows, h = b * s, 32
+    inp = rng.uniform(-1, 1, (rows, h)).astype(np.float32)
+    gamma, beta = rng.uniform(-1, 1, h).astype(np.float32), rng.uniform(-1, 1, h).astype(np.float32)
+    dy = rng.uniform(-1, 1, (rows, h)).astype(np.float32)
+    outs = []
+    for fused in (True, False):
+        x, g_, b_ = mk(inp, True), mk(gamma, True), mk(beta, True)
+        if fused:
+            y = x.layernorm(g_, b_)
+        else:
+            mean = x.mean(dim=1).view(rows, 1)
+            var = x.var(dim=1).view(rows, 1)
+            y = g_ * ((x - mean) / ((var + 1e-8) ** 0.5)) + b_
+        y.backward(mk(dy))
+        outs.append((y.to_numpy(), x.grad.to_numpy(), g_.grad.to_numpy().reshape(h), b_.grad.to_numpy().reshape(h)))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], atol=1e-2, rtol=1e-3)
+    for got, want in zip(outs[0][1:], outs[1][1:]):
+        np.testing.assert_allclose(got, want, atol=1e-3 * max(1.0, float(np.abs(want).max())), rtol=1e-2)
