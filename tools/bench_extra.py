@@ -155,6 +155,18 @@ def main():
     if "sweep" in what:  # BASELINE.json config #3: fwd sweep, batch 8, 16 heads
         doc["fwd_sweep"] = [attn_case(P, 8, 16, N, d, c) for d in (128, 64) for c in (False, True)
                             for N in (512, 1024, 2048, 4096, 8192)]
+    if "seqsweep" in what:   # the BASELINE metric itself: fwd+bwd TFLOP/s vs sequence length (32 heads, batch 8)
+        doc["fwdbwd_vs_seq"] = []
+        for d in (128, 64):
+            for c in (False, True):
+                for N in (512, 1024, 2048, 4096, 8192):
+                    r = attn_case(P, 8, 32, N, d, c, bwd=True, reps=6)
+                    tot = (r["fwd_ms"] + r["bwd_ms"]) * 1e-3
+                    fl = r["fwd_tflops"] * r["fwd_ms"] * 1e-3 + r["bwd_tflops"] * r["bwd_ms"] * 1e-3
+                    r["fwdbwd_tflops"] = fl / tot
+                    r["fwdbwd_frac_sustained"] = r["fwdbwd_tflops"] / P["tf_sustained"]
+                    r["fwdbwd_frac_datasheet"] = r["fwdbwd_tflops"] / 2250.0
+                    doc["fwdbwd_vs_seq"].append(r)
     if "cfg4" in what:   # config #4 geometry: fwd+bwd, 32 heads, N=4096, d=128, +- causal, +- padding
         doc["cfg4"] = [attn_case(P, 8, 32, 4096, 128, c, kv, bwd=True) for c in (False, True) for kv in (False, True)]
     txt = json.dumps(doc, indent=1)
