@@ -139,6 +139,31 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off (if the cpuset allows), so the pinned host buffers
+    of the end-to-end leg are first-touched on that node and the DMA does not cross the socket interconnect.
+    Returns a short description for the JSON line (None when nothing was changed)."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True, timeout=20).strip().lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed or allowed == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"node{node}:{len(allowed)}cpus"
+    except Exception:
+        return None
+
+
 def _agg(dist):
     from flashattn_b200.sharding import Aggregator
     return Aggregator(dist, "cuda")
@@ -214,6 +239,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     rank, world, local, dist = dist_setup(args.gpus)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     import flashattn_b200 as fb
     from flashattn_b200 import device as dev
     lib = fb._lib.load("flashattention_kernel")
@@ -329,6 +355,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
+            "numa_binding_rank0": numa,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
