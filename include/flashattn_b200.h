@@ -196,6 +196,12 @@ int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, cons
  *   fa_softmax_xent_fw_dev: loss (n) = logsumexp(logits (n,C)) - logits[i, t_i]; lse (n) saved for the backward;
  *                           logsumexp = max + log(sum + 1e-6), minitorch's log (operators.py:107-110)
  *   fa_softmax_xent_bw_dev: dlogits = dloss[i] * (exp(logits - lse[i]) - [j == t_i]) */
+/* host-pointer variants (staged through the device pool, synchronous, status via fa_last_status) */
+void launch_embedding_fw(float* out, const float* ids, const float* W, long long n, int V, int E);
+void launch_embedding_bw(float* dW, const float* ids, const float* dout, long long n, int V, int E);
+void launch_softmax_xent_fw(float* loss, float* lse, const float* logits, const float* targets, long long n, int C);
+void launch_softmax_xent_bw(float* dlogits, const float* dloss, const float* logits, const float* targets,
+                            const float* lse, long long n, int C);
 int fa_embedding_fw_dev(float* out, const float* ids, const float* W, long long n, int V, int E, fa_stream_t stream);
 int fa_embedding_bw_dev(float* dW, const float* ids, const float* dout, long long n, int V, int E, fa_stream_t stream);
 int fa_softmax_xent_fw_dev(float* loss, float* lse, const float* logits, const float* targets, long long n, int C,

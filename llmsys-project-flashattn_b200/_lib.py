@@ -110,6 +110,10 @@ SYMBOLS["combine"] = {
                            c_void_p]),
     "fa_reduce_dev": (c_int, [c_void_p, _i32, _i32, c_void_p, _i32, _i32, c_int, c_int, c_double, c_int, c_void_p]),
     "fa_matmul_dev": (c_int, [c_void_p, _i32, _i32, c_void_p, _i32, _i32, c_void_p, _i32, _i32, c_void_p]),
+    "launch_embedding_fw": (None, [_f32, _f32, _f32, c_longlong, c_int, c_int]),
+    "launch_embedding_bw": (None, [_f32, _f32, _f32, c_longlong, c_int, c_int]),
+    "launch_softmax_xent_fw": (None, [_f32, _f32, _f32, _f32, c_longlong, c_int]),
+    "launch_softmax_xent_bw": (None, [_f32, _f32, _f32, _f32, _f32, c_longlong, c_int]),
     "fa_embedding_fw_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "fa_embedding_bw_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "fa_softmax_xent_fw_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),

@@ -659,4 +659,59 @@ int fa_softmax_xent_bw_dev(float* dlogits, const float* dloss, const float* logi
   return FA_OK;
 }
 
+// Host-pointer variants of the lookup / loss ops (same staging pattern as tensorMap etc.: grow-only device pool,
+// synchronous) so that reference-style host-storage tensors can use them too.
+static bool stage_in(float** d, int slot, const float* h, size_t count) {
+  *d = static_cast<float*>(g_pool.get(slot, sizeof(float) * (count ? count : 1)));
+  if (!*d) return false;
+  return count == 0 || cudaMemcpyAsync(*d, h, sizeof(float) * count, cudaMemcpyHostToDevice, 0) == cudaSuccess;
+}
+void launch_embedding_fw(float* out, const float* ids, const float* W, long long n, int V, int E) {
+  clear_error();
+  float *d_out, *d_ids, *d_w;
+  if (n < 0 || V <= 0 || E <= 0) { set_error(FA_ERR_INVALID, "launch_embedding_fw: bad shape"); return; }
+  if (n == 0) return;
+  d_out = static_cast<float*>(g_pool.get(0, sizeof(float) * n * E));
+  if (!d_out || !stage_in(&d_ids, 1, ids, n) || !stage_in(&d_w, 2, W, (size_t)V * E)) CB_FAIL("launch_embedding_fw: staging failed");
+  if (fa_embedding_fw_dev(d_out, d_ids, d_w, n, V, E, nullptr) != FA_OK) return;
+  CB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * n * E, cudaMemcpyDeviceToHost, 0));
+  CB_CUDA(cudaStreamSynchronize(0));
+}
+void launch_embedding_bw(float* dW, const float* ids, const float* dout, long long n, int V, int E) {
+  clear_error();
+  float *d_dw, *d_ids, *d_g;
+  if (n < 0 || V <= 0 || E <= 0) { set_error(FA_ERR_INVALID, "launch_embedding_bw: bad shape"); return; }
+  d_dw = static_cast<float*>(g_pool.get(0, sizeof(float) * (size_t)V * E));
+  if (!d_dw || !stage_in(&d_ids, 1, ids, n) || !stage_in(&d_g, 2, dout, (size_t)n * E)) CB_FAIL("launch_embedding_bw: staging failed");
+  if (fa_embedding_bw_dev(d_dw, d_ids, d_g, n, V, E, nullptr) != FA_OK) return;
+  CB_CUDA(cudaMemcpyAsync(dW, d_dw, sizeof(float) * (size_t)V * E, cudaMemcpyDeviceToHost, 0));
+  CB_CUDA(cudaStreamSynchronize(0));
+}
+void launch_softmax_xent_fw(float* loss, float* lse, const float* logits, const float* targets, long long n, int C) {
+  clear_error();
+  float *d_x, *d_t;
+  if (n < 0 || C <= 0) { set_error(FA_ERR_INVALID, "launch_softmax_xent_fw: bad shape"); return; }
+  if (n == 0) return;
+  float* d_out = static_cast<float*>(g_pool.get(0, sizeof(float) * 2 * n));
+  if (!d_out || !stage_in(&d_x, 1, logits, (size_t)n * C) || !stage_in(&d_t, 2, targets, n)) CB_FAIL("launch_softmax_xent_fw: staging failed");
+  if (fa_softmax_xent_fw_dev(d_out, d_out + n, d_x, d_t, n, C, nullptr) != FA_OK) return;
+  CB_CUDA(cudaMemcpyAsync(loss, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, 0));
+  CB_CUDA(cudaMemcpyAsync(lse, d_out + n, sizeof(float) * n, cudaMemcpyDeviceToHost, 0));
+  CB_CUDA(cudaStreamSynchronize(0));
+}
+void launch_softmax_xent_bw(float* dlogits, const float* dloss, const float* logits, const float* targets, const float* lse,
+                            long long n, int C) {
+  clear_error();
+  float *d_g, *d_x, *d_t, *d_l;
+  if (n < 0 || C <= 0) { set_error(FA_ERR_INVALID, "launch_softmax_xent_bw: bad shape"); return; }
+  if (n == 0) return;
+  float* d_dx = static_cast<float*>(g_pool.get(0, sizeof(float) * (size_t)n * C));
+  if (!d_dx || !stage_in(&d_x, 1, logits, (size_t)n * C) || !stage_in(&d_t, 2, targets, n) || !stage_in(&d_g, 3, dloss, n) ||
+      !stage_in(&d_l, 4, lse, n))
+    CB_FAIL("launch_softmax_xent_bw: staging failed");
+  if (fa_softmax_xent_bw_dev(d_dx, d_g, d_x, d_t, d_l, n, C, nullptr) != FA_OK) return;
+  CB_CUDA(cudaMemcpyAsync(dlogits, d_dx, sizeof(float) * (size_t)n * C, cudaMemcpyDeviceToHost, 0));
+  CB_CUDA(cudaStreamSynchronize(0));
+}
+
 }  // extern "C"

@@ -295,6 +295,47 @@ class CudaKernelOps:
         _lib.check(lib)
         return inp_grad, gamma_grad, beta_grad
 
+    # ------------------------------------------------------------------ embedding lookup / cross-entropy
+    @staticmethod
+    def embedding_fw(ids, weights):
+        lib = _lib.load("combine")
+        ids, weights = ids.contiguous(), weights.contiguous()
+        V, E = weights.shape
+        out = weights.zeros(tuple(ids.shape) + (E,))
+        lib.launch_embedding_fw(_storage(out), _storage(ids), _storage(weights), _size(ids), V, E)
+        _lib.check(lib)
+        return out
+
+    @staticmethod
+    def embedding_bw(ids, out_grad, num_embeddings: int):
+        lib = _lib.load("combine")
+        ids, out_grad = ids.contiguous(), out_grad.contiguous()
+        E = out_grad.shape[-1]
+        dW = out_grad.zeros((num_embeddings, E))
+        lib.launch_embedding_bw(_storage(dW), _storage(ids), _storage(out_grad), _size(ids), num_embeddings, E)
+        _lib.check(lib)
+        return dW
+
+    @staticmethod
+    def softmax_xent_fw(logits, target):
+        lib = _lib.load("combine")
+        logits, target = logits.contiguous(), target.contiguous()
+        n, C = logits.shape
+        loss, lse = logits.zeros((n,)), logits.zeros((n,))
+        lib.launch_softmax_xent_fw(_storage(loss), _storage(lse), _storage(logits), _storage(target), n, C)
+        _lib.check(lib)
+        return loss, lse
+
+    @staticmethod
+    def softmax_xent_bw(out_grad, logits, target, lse):
+        lib = _lib.load("combine")
+        out_grad, logits, target, lse = (t.contiguous() for t in (out_grad, logits, target, lse))
+        n, C = logits.shape
+        dx = logits.zeros((n, C))
+        lib.launch_softmax_xent_bw(_storage(dx), _storage(out_grad), _storage(logits), _storage(target), _storage(lse), n, C)
+        _lib.check(lib)
+        return dx
+
     # ------------------------------------------------------------------ mode switch
     @staticmethod
     def set_flash_mode(mode: str) -> None:

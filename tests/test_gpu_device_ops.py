@@ -203,3 +203,34 @@ def test_decoder_lm_golden_with_fused_embedding_and_loss():
         if k.startswith("g:"):
             got = params[k[2:]].value.grad.to_numpy()
             np.testing.assert_allclose(got, z[k], atol=2e-5 * max(1.0, float(np.abs(z[k]).max())), rtol=2e-4, err_msg=k)
+
+
+def test_fused_lookup_and_loss_through_host_pointer_ops_equal_device_ops():
+    """CudaKernelOps.embedding_* / softmax_xent_* (host-pointer launch_* symbols) give the same bits as the
+    device-resident ops, and the DecoderLM golden holds with them on reference-style host storage."""
+    rng = np.random.default_rng(21)
+    V, E, n, C = 50, 24, 77, 130
+    W = rng.standard_normal((V, E)).astype(np.float32)
+    ids = rng.integers(0, V, (7, 11))
+    dout = rng.standard_normal((7, 11, E)).astype(np.float32)
+    x = (rng.standard_normal((n, C)) * 2).astype(np.float32)
+    t = rng.integers(0, C, (n,))
+    g = rng.standard_normal((n,)).astype(np.float32)
+    res = []
+    for backend in (fb.default_backend(), DEV):
+        mk = lambda a, r=False: fb.tensor_from_numpy(np.asarray(a, np.float32), backend=backend, requires_grad=r)
+        w, lx = mk(W, True), mk(x, True)
+        emb = fb.EmbeddingLookup.apply(mk(ids), w)
+        emb.backward(mk(dout))
+        loss = fb.softmax_loss(lx, mk(t), fused=True)
+        loss.backward(mk(g))
+        res.append((emb.to_numpy(), w.grad.to_numpy(), loss.to_numpy(), lx.grad.to_numpy()))
+    for a, b in zip(*res):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(res[0][0], W[ids])
+    z = np.load(golden("decoder_small.npz")[0])
+    fb.CudaKernelOps.set_flash_mode("fp32")
+    model, params = load_decoder(z, backend=fb.default_backend(), use_flash_attention=True, use_fused_embedding=True)
+    logits, total = decoder_loss(model, z, backend=fb.default_backend(), fused_loss=True)
+    np.testing.assert_allclose(logits.to_numpy(), z["logits"], atol=2e-4, rtol=2e-5)
+    assert abs(float(total.to_numpy().reshape(-1)[0]) - float(z["loss"][0])) < 2e-5
