@@ -382,6 +382,8 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
     r = B * H * N
 
     def pinned(count):
+        if os.environ.get("BENCH_E2E_PAGEABLE") == "1":     # what a numpy-backed minitorch tensor hands over
+            return None, np.empty(count, dtype=np.float32)
         p = lib.fa_malloc_host(count * 4)
         if not p:
             raise MemoryError("pinned allocation failed")
@@ -425,13 +427,15 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
     total = reduce_sum(dist, flops_step * steps)
     lib.fa_set_mode(fb._lib.FA_MODE_FP32)
     for p, _ in list(bufs.values()) + list(stats.values()):
-        lib.fa_free_host(p)
+        if p:
+            lib.fa_free_host(p)
     h2d = (3 * n + 5 * n + 2 * r) * 4 + (mask.nbytes * 2 if mask is not None else 0)   # fwd: Q,K,V; bwd: Q,K,V,O,dO,m,l
     d2h = (n + 2 * r + 3 * n) * 4
     return {"value": total / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": dt / steps * 1e3, "batch_per_gpu": B,
             "path": "launch_flashattention_forward_masked + launch_flashattention_backward_masked (legacy C ABI, "
-                    "fp32 pinned host buffers, FA_MODE_BF16), wall clock incl. H2D/D2H"}
+                    "fp32 %s host buffers, FA_MODE_BF16), wall clock incl. H2D/D2H" % (
+                        "pageable" if os.environ.get("BENCH_E2E_PAGEABLE") == "1" else "pinned")}
 
 
 if __name__ == "__main__":
