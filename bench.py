@@ -12,9 +12,18 @@ FLOPs of all ranks / max-over-ranks device time.
 
 Timing: CUDA events on the launching (default) stream, W warm-up steps, K timed steps bracketed
 by barrier + device sync; inputs (8 x 268 MB) exceed the 126 MB L2, so no explicit flush.
-`e2e` = the same step through the reference-facing legacy C ABI (host fp32 buffers in pinned
-memory, H2D/D2H inside the timed region).  `cpu_baseline` = the reference's composed numba CPU
-path (oracle port) on a bounded sample, rank 0 only.
+`roofline.peak` is the measured cuBLAS bf16 figure of the matching regime: the BURST figure when the
+timed region is shorter than one second, the SUSTAINED (power-capped) one otherwise; both fractions
+are printed, labelled, and nothing is crossed.
+`e2e` = the same step through the reference-facing operator surface -- CudaKernelOps.flash_attention_fw /
+_bw(key_mask=...) on numpy-backed tensors, i.e. the legacy host-pointer C ABI with pageable fp32 host
+buffers, H2D/D2H inside the timed region; `e2e_pinned` = the same symbols called by raw ctypes on
+page-locked buffers.  `cpu_baseline` = the reference's own composed attention on its numba CPU backend
+(overlay tree baseline/_ref, kind "reference"; the oracle port when the overlay is absent) on a
+bounded sample, rank 0 only.
+At N=1 the line also carries `sweep` (BASELINE config #3: fwd TFLOP/s over seq 512..8192 x head_dim
+64/128 x causal) and `companions` (fused softmax / layernorm GB/s against the measured HBM peak);
+at N>1 it carries `cfg5` (config #5, strong scaling of global B=64 N=8192) and `per_rank_ms`.
 """
 from __future__ import annotations
 
@@ -46,17 +55,19 @@ WORKLOADS = {
                         desc="config #5 with a causal mask"),
     "small": dict(B=2, H=4, N=1024, d=128, causal=False, padding=True, desc="smoke-sized workload"),
 }
-CPU_SAMPLE = dict(B=2, H=32, N=512, d=128)  # bounded sample of the same op for the CPU arms
+CPU_SAMPLE = dict(B=2, H=32, N=512, d=128)      # bounded sample of the same op for the numba port
+CPU_SAMPLE_REF = dict(B=1, H=8, N=512, d=128)   # ... and for the reference's own minitorch FastOps path (~2 GFLOP/s)
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_kernel_shares.json")
-    try:
-        with open(path) as f:
-            return float(json.load(f)["dram_traffic_bytes_per_launch"][kernel])
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel from the newest committed ncu capture (profiles/), or None."""
+    for name in ("r02_kernel_shares.json", "r01_kernel_shares.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["dram_traffic_bytes_per_launch"][kernel]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def load_peaks():
@@ -64,9 +75,9 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), burst=float(p["bf16_tflops"]),
-                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)")
-    return dict(tflops=1590.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+        return dict(sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), burst=float(p["bf16_tflops"]),
+                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, cuBLAS bf16 8192^3)")
+    return dict(sustained=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -181,6 +192,28 @@ def reduce_sum(dist, x):
     return _agg(dist).sum(x)
 
 
+def cpu_overlay_run(steps, warmup):
+    """The reference's OWN composed attention on its numba CPU backend, from the overlay tree (baseline/_ref)."""
+    script = os.path.join(ROOT, "baseline", "ref_cpu_attention.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "minitorch")):
+        return None, None
+    c = CPU_SAMPLE_REF
+    env = dict(os.environ, NUMBA_DISABLE_CUDA="1")
+    env.pop("NUMBA_NUM_THREADS", None)
+    try:
+        out = subprocess.run([sys.executable, script] + [str(c[k]) for k in "BHNd"] + [str(steps), str(warmup)],
+                             env=env, capture_output=True, text=True, timeout=900)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:  # noqa: BLE001
+        print(f"bench.py: overlay CPU arm failed ({ex}); using the oracle port", file=sys.stderr)
+        return None, None
+    dt = r["seconds_per_step"]
+    flops = 14.0 * c["B"] * c["H"] * c["N"] * c["N"] * c["d"]
+    return dict(value=flops / dt / 1e12, unit="TFLOP/s", cores=int(r["cores"]), kind="reference",
+                sample=f"reference minitorch composed attention (FastOps, numba parallel) fwd+bwd fp32, B={c['B']} "
+                       f"H={c['H']} N={c['N']} d={c['d']}, {steps} runs, {dt * 1e3:.0f} ms each"), dt
+
+
 def cpu_reference_run(steps, warmup, cores=None):
     """The reference's composed attention on the host cores (oracle port), bounded sample."""
     import numba
@@ -206,21 +239,79 @@ def cpu_reference_run(steps, warmup, cores=None):
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    cb, dt = cpu_reference_run(steps, min(args.warmup, 1) or 1)
+    steps = max(1, min(args.steps, 3))
+    cb, dt = cpu_overlay_run(steps, 1)
+    note = ("the reference's own minitorch composed attention on its numba CPU backend (FastOps), run unmodified "
+            "from the overlay tree baseline/_ref")
+    if cb is None:
+        cb, dt = cpu_reference_run(steps, 1)
+        note = "overlay tree absent: numba port of the reference's composed attention (oracle/numba_composed.py)"
     w = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": "attention fwd+bwd TFLOP/s", "value": cb["value"], "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "sample": cb["sample"],
-                   "note": "reference's numba CPU composed attention (oracle port: oracle/numba_composed.py); "
-                           "the reference's CUDA flash kernel does not compile (SURVEY.md 2.3)"},
+                   "note": note + "; the reference's CUDA flash kernel does not compile (SURVEY.md 2.3)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gather(dist, x):
+    return _agg(dist).gather(x)
+
+
+def make_inputs(fb, dev, lib, B, H, N, d, seeds):
+    """Synthetic device-resident bf16 tensors: one N(0,1) (H,N,d) slice per tensor, replicated over the batch (the
+    kernels' work does not depend on the values; generating 4 x 268 MB..4 GB of normals on the host would dominate
+    the run)."""
+    outs = []
+    per = H * N * d
+    for seed in seeds:
+        a = dev.DeviceArray((B, H, N, d), "bf16")
+        base = dev.to_bf16_bits(np.random.default_rng(seed).standard_normal(per, dtype=np.float32))
+        for b in range(B):
+            fb._lib.check(lib, lib.fa_h2d(ctypes.c_void_p(a.ptr + b * per * 2), base.ctypes.data_as(ctypes.c_void_p),
+                                          per * 2))
+        outs.append(a)
+    return outs
+
+
+def timed_steps(lib, dev, dist, fwd, bwd, steps, warmup):
+    """`warmup` untimed steps, then `steps` timed ones with an event around every fwd and bwd; returns
+    (total_ms of this rank, mean fwd_ms, mean bwd_ms, kernels launched)."""
+    for _ in range(warmup):
+        fwd()
+        bwd()
+    dev.sync()
+    ev = [[lib.fa_event_create() for _ in range(3)] for _ in range(steps)]
+    launches0 = lib.fa_launch_count()
+    barrier(dist)
+    dev.sync()
+    for i in range(steps):
+        lib.fa_event_record(ev[i][0], None)
+        fwd()
+        lib.fa_event_record(ev[i][1], None)
+        bwd()
+        lib.fa_event_record(ev[i][2], None)
+    dev.sync()
+    barrier(dist)
+    launches = int(lib.fa_launch_count() - launches0)
+    total_ms = lib.fa_event_elapsed_ms(ev[0][0], ev[-1][2])
+    fwd_ms = float(np.mean([lib.fa_event_elapsed_ms(e[0], e[1]) for e in ev]))
+    bwd_ms = float(np.mean([lib.fa_event_elapsed_ms(e[1], e[2]) for e in ev]))
+    for e3 in ev:
+        for e in e3:
+            lib.fa_event_destroy(e)
+    return float(total_ms), fwd_ms, bwd_ms, launches
+
+
+def fracs(tf, peaks):
+    return {"of_measured_burst": tf / peaks["burst"], "of_measured_sustained": tf / peaks["sustained"],
+            "of_datasheet_2250": tf / 2250.0}
 
 
 def main():
@@ -232,6 +323,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip sweep / companions (N=1) and cfg5 (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
@@ -257,18 +349,7 @@ def main():
     rng = np.random.default_rng(1000 + rank)
     kv_len = rng.integers(N // 2, N + 1, B).astype(np.int32) if w["padding"] else None
 
-    # ---- synthetic device-resident inputs (bf16), generated per (b) slice to bound host memory
-    def dev_randn(seed):
-        out = dev.DeviceArray((B, H, N, d), "bf16")
-        r = np.random.default_rng(seed)
-        per = H * N * d
-        for b in range(B):
-            chunk = dev.to_bf16_bits(r.standard_normal(per, dtype=np.float32))
-            fb._lib.check(lib, lib.fa_h2d(ctypes.c_void_p(out.ptr + b * per * 2), chunk.ctypes.data_as(ctypes.c_void_p),
-                                          per * 2))
-        return out
-
-    Q, K, V, dO = (dev_randn(10 * rank + i) for i in range(4))
+    Q, K, V, dO = make_inputs(fb, dev, lib, B, H, N, d, [10 * rank + i for i in range(4)])
     dkv = dev.DeviceArray.from_numpy(kv_len) if kv_len is not None else None
     O = dev.DeviceArray((B, H, N, d), "bf16")
     m, l = dev.DeviceArray((B, H, N), "f32"), dev.DeviceArray((B, H, N), "f32")
@@ -278,61 +359,76 @@ def main():
     flops_b = dev.attn_flops(B, H, N, d, causal, kv_len, backward=True)
     flops_nominal = 14.0 * B * H * N * N * d * (0.5 if causal else 1.0)
 
-    def step():
+    def fwd():
         dev.flash_fwd(Q, K, V, causal=causal, kv_len=dkv, out=(O, m, l))
+
+    def bwd():
         dev.flash_bwd(Q, K, V, O, dO, m, l, causal=causal, kv_len=dkv, out=grads)
 
     sampler = ClockSampler(local)
     sampler.start()           # started before the warm-up: nvidia-smi needs ~1 s to emit its first line
-    for _ in range(args.warmup):
-        step()
-    dev.sync()
-
-    # ---- timed region: K steps, events around every fwd and bwd
-    ev = [[lib.fa_event_create() for _ in range(3)] for _ in range(args.steps)]
-    launches0 = lib.fa_launch_count()
-    barrier(dist)
+    for _ in range(3):
+        fwd()
+        bwd()
     dev.sync()
     mark = sampler.mark()
-    for i in range(args.steps):
-        lib.fa_event_record(ev[i][0], None)
-        dev.flash_fwd(Q, K, V, causal=causal, kv_len=dkv, out=(O, m, l))
-        lib.fa_event_record(ev[i][1], None)
-        dev.flash_bwd(Q, K, V, O, dO, m, l, causal=causal, kv_len=dkv, out=grads)
-        lib.fa_event_record(ev[i][2], None)
-    dev.sync()
-    barrier(dist)
-    launches = int(lib.fa_launch_count() - launches0)
+    total_ms_local, fwd_ms, bwd_ms, launches = timed_steps(lib, dev, dist, fwd, bwd, args.steps, args.warmup)
     probe = 0
     t_probe = time.perf_counter()
     while sampler.mark() - mark < 4 and time.perf_counter() - t_probe < 3.0:
-        step()          # short timed regions: keep the same load running (untimed) until nvidia-smi has sampled it
+        fwd()           # short timed regions: keep the same load running (untimed) until nvidia-smi has sampled it
+        bwd()
         dev.sync()
         probe += 1
     clocks = sampler.stop(mark)
     clocks["untimed_probe_steps"] = probe
-    total_ms = lib.fa_event_elapsed_ms(ev[0][0], ev[-1][2])
-    fwd_ms = float(np.mean([lib.fa_event_elapsed_ms(e[0], e[1]) for e in ev]))
-    bwd_ms = float(np.mean([lib.fa_event_elapsed_ms(e[1], e[2]) for e in ev]))
-    total_ms = reduce_max(dist, total_ms)
+    per_rank_ms = gather(dist, total_ms_local / args.steps)
+    per_rank_fwd = gather(dist, fwd_ms)
+    per_rank_bwd = gather(dist, bwd_ms)
+    total_ms = reduce_max(dist, total_ms_local)
     all_flops = reduce_sum(dist, (flops_f + flops_b) * args.steps)
     ms_per_step = total_ms / args.steps
     value = all_flops / (total_ms * 1e-3) / 1e12
 
-    # ---- end to end through the legacy (reference-facing) host-pointer ABI
-    e2e = None
+    # ---- config #5 (strong scaling, global B=64 N=8192) when several GPUs share the job
+    cfg5 = None
+    if world > 1 and not args.no_extras and args.workload == "cfg4":
+        del Q, K, V, dO, O, m, l, grads
+        cfg5 = run_cfg5(fb, dev, lib, dist, rank, world)
+
+    # ---- end to end through the reference-facing operator surface / legacy host-pointer ABI
+    e2e = e2e_pinned = None
     if not args.no_e2e:
-        e2e = run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_f + flops_b, min(args.steps, 3), dist)
+        e2e = run_e2e(fb, lib, B, H, N, d, causal, kv_len, min(args.steps, 3), dist, "ops")
+        e2e_pinned = run_e2e(fb, lib, B, H, N, d, causal, kv_len, min(args.steps, 3), dist, "pinned")
+
+    sweep = companions = None
+    if world == 1 and not args.no_extras and args.workload == "cfg4":
+        from tools import bench_extra as X
+        P2 = X.peaks()
+        sweep = [X.attn_case(P2, 8, 16, n_, d_, c_, reps=5, quiet=True) for d_ in (128, 64) for c_ in (False, True)
+                 for n_ in (512, 1024, 2048, 4096, 8192)]
+        companions = X.companions(P2, quiet=True)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu_baseline, _ = cpu_reference_run(3, 1)
+        cpu_baseline, _ = cpu_overlay_run(2, 1)
+        port, _ = cpu_reference_run(3, 1)
+        if cpu_baseline is None:
+            cpu_baseline = port
+        else:
+            cpu_baseline["port_value"] = port["value"]
+            cpu_baseline["port_sample"] = port["sample"]
 
     if rank == 0:
         fwd_tf = flops_f / (fwd_ms * 1e-3) / 1e12
         bwd_tf = flops_b / (bwd_ms * 1e-3) / 1e12
         dom = "bwd" if bwd_ms >= fwd_ms else "fwd"
         dom_tf = bwd_tf if dom == "bwd" else fwd_tf
+        timed_s = total_ms * 1e-3
+        regime = "burst" if timed_s < 1.0 else "sustained"
+        peak = peaks[regime]
+        traffic, traffic_src = ncu_traffic(f"{dom}_kernel") if args.workload == "cfg4" else (None, None)
         line = {
             "metric": "attention fwd+bwd TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -343,34 +439,68 @@ def main():
                        "nominal_tflops": flops_nominal * world / (ms_per_step * 1e-3) / 1e12,
                        "l2": "inputs larger than L2 (8 tensors x 268 MB per GPU); no flush needed"},
             "roofline": {"bound": "tensor", "kernel": f"sm100::{dom}_kernel (tcgen05/TMEM), timed with its pre/post passes",
-                         "achieved": dom_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": dom_tf / peaks["tflops"],
-                         "traffic": ncu_traffic(f"{dom}_kernel") if args.workload == "cfg4" else None,
-                         "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_kernel_shares.json)",
+                         "achieved": dom_tf, "peak": peak, "unit": "TFLOP/s", "frac": dom_tf / peak,
+                         "regime": f"{regime}: timed region {timed_s:.2f} s -> measured {regime} cuBLAS bf16 peak",
+                         "frac_of_measured_burst": dom_tf / peaks["burst"],
+                         "frac_of_measured_sustained": dom_tf / peaks["sustained"],
+                         "traffic": traffic, "traffic_unit": f"bytes/launch (ncu dram read+write, profiles/{traffic_src})",
                          "peak_source": peaks["source"]},
-            "kernels": {"fwd_ms": fwd_ms, "fwd_tflops": fwd_tf, "fwd_frac_measured_sustained": fwd_tf / peaks["tflops"],
-                        "fwd_frac_measured_burst": fwd_tf / peaks["burst"], "fwd_frac_datasheet_2250": fwd_tf / 2250.0,
-                        "bwd_ms": bwd_ms, "bwd_tflops": bwd_tf, "bwd_frac_measured_sustained": bwd_tf / peaks["tflops"],
-                        "bwd_frac_measured_burst": bwd_tf / peaks["burst"], "bwd_frac_datasheet_2250": bwd_tf / 2250.0},
+            "kernels": {"fwd_ms": fwd_ms, "fwd_tflops": fwd_tf, "fwd_frac": fracs(fwd_tf, peaks),
+                        "bwd_ms": bwd_ms, "bwd_tflops": bwd_tf, "bwd_frac": fracs(bwd_tf, peaks), "regime": regime},
+            "per_rank_ms": {"step": per_rank_ms, "fwd": per_rank_fwd, "bwd": per_rank_bwd},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
+            "e2e_pinned": e2e_pinned,
             "gpu_launches": launches,
             "clocks": clocks,
             "numa_binding_rank0": numa,
         }
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
+        if sweep is not None:
+            line["sweep"] = sweep
+            line["companions"] = companions
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
-    """Same step through launch_flashattention_{forward,backward}_masked (host fp32 buffers, pinned)."""
-    # 8 pinned fp32 tensors per rank (4.3 GB at cfg4): with several ranks on one host, keep the total pinned
-    # footprint under ~40 % of the available host memory by shrinking this rank's e2e batch if necessary.
+def run_cfg5(fb, dev, lib, dist, rank, world):
+    """BASELINE config #5: global batch 64 x 32 heads x seq 8192 x d 128 (bf16) split by batch over the ranks (strong
+    scaling, no collective): whole-job TFLOP/s = FLOPs of all ranks / max-over-ranks device time."""
+    from flashattn_b200.sharding import shard_batch
+    Bg, H, N, d = 64, 32, 8192, 128
+    b0, b1 = shard_batch(Bg, world, rank)
+    B = max(1, b1 - b0)
+    Q, K, V, dO = make_inputs(fb, dev, lib, B, H, N, d, [100 + i for i in range(4)])
+    O = dev.DeviceArray((B, H, N, d), "bf16")
+    m, l = dev.DeviceArray((B, H, N), "f32"), dev.DeviceArray((B, H, N), "f32")
+    grads = tuple(dev.DeviceArray((B, H, N, d), "bf16") for _ in range(3))
+    ff = dev.attn_flops(B, H, N, d, False, None, backward=False)
+    fbw = dev.attn_flops(B, H, N, d, False, None, backward=True)
+    steps = 3
+    tot, fwd_ms, bwd_ms, _ = timed_steps(
+        lib, dev, dist, lambda: dev.flash_fwd(Q, K, V, out=(O, m, l)),
+        lambda: dev.flash_bwd(Q, K, V, O, dO, m, l, out=grads), steps, 2)
+    per_rank = gather(dist, tot / steps)
+    tmax = reduce_max(dist, tot)
+    allf = reduce_sum(dist, (ff + fbw) * steps)
+    return {"workload": "config #5: global B=64 H=32 N=8192 d=128 bf16 fwd+bwd, batch-sharded (strong scaling)",
+            "value": allf / (tmax * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world, "steps": steps,
+            "ms_per_step": tmax / steps, "batch_per_gpu": B, "per_rank_ms": per_rank,
+            "rank0_fwd_tflops": ff / (fwd_ms * 1e-3) / 1e12, "rank0_bwd_tflops": fbw / (bwd_ms * 1e-3) / 1e12}
+
+
+def run_e2e(fb, lib, B, H, N, d, causal, kv_len, steps, dist, path):
+    """The same step with HOST fp32 buffers, copies inside the timed region (wall clock, max over ranks).
+    path == "ops":    CudaKernelOps.flash_attention[_causal]_fw / _bw(key_mask=...) on numpy-backed tensors -- the call a
+                      minitorch user makes (pageable inputs; outputs allocated by the operator);
+    path == "pinned": launch_flashattention_{forward,backward}_masked by raw ctypes on page-locked buffers."""
     from flashattn_b200 import device as dev
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    try:
-        avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
-        per_b = 8 * H * N * d * 4 + 2 * H * N * 4
+    try:    # several ranks share one host: keep the host footprint under ~40 % of the available memory
+        avail = next(int(ln.split()[1]) * 1024 for ln in open("/proc/meminfo") if ln.startswith("MemAvailable"))
+        per_b = 10 * H * N * d * 4
         B = max(1, min(B, int(0.4 * avail / world / per_b)))
     except Exception:
         pass
@@ -380,40 +510,53 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
         dev.attn_flops(B, H, N, d, causal, kv_len, backward=True)
     n = B * H * N * d
     r = B * H * N
-
-    def pinned(count):
-        if os.environ.get("BENCH_E2E_PAGEABLE") == "1":     # what a numpy-backed minitorch tensor hands over
-            return None, np.empty(count, dtype=np.float32)
-        p = lib.fa_malloc_host(count * 4)
-        if not p:
-            raise MemoryError("pinned allocation failed")
-        return p, np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(count,))
-
-    bufs = {k: pinned(n) for k in ("Q", "K", "V", "O", "dO", "dQ", "dK", "dV")}
-    stats = {k: pinned(r) for k in ("l", "m")}
-    rng = np.random.default_rng(5)
-    for k in ("Q", "K", "V", "dO"):
-        a = bufs[k][1]
-        step_ = 1 << 24
-        for s in range(0, n, step_):
-            a[s:s + step_] = rng.standard_normal(min(step_, n - s), dtype=np.float32)
     mask = None
-    mptr = None
     if kv_len is not None:
         mask = np.where(np.arange(N)[None, :] < kv_len[:, None], 0.0, -1e8).astype(np.float32)
-        mptr = mask.ctypes.data_as(ctypes.c_void_p)
-    lib.fa_set_mode(fb._lib.FA_MODE_BF16)
-    A = {k: v[1] for k, v in bufs.items()}
-    S = {k: v[1] for k, v in stats.items()}
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal(H * N * d, dtype=np.float32)
 
-    def step():
-        lib.launch_flashattention_forward_masked(A["Q"], A["K"], A["V"], A["O"], S["l"], S["m"], mptr, int(causal),
-                                                 B, H, N, d)
-        fb._lib.check(lib)
-        lib.launch_flashattention_backward_masked(A["Q"], A["K"], A["V"], A["O"], A["dQ"], A["dK"], A["dV"], A["dO"],
-                                                  S["l"], S["m"], mptr, int(causal), B, H, N, d)
-        fb._lib.check(lib)
-        return float(A["dQ"][0])  # the step's result is read on the host
+    def fill(a):
+        a.reshape(B, -1)[:] = base[None, :]
+        return a
+
+    hits0, miss0 = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib.fa_forward_cache_stats(ctypes.byref(hits0), ctypes.byref(miss0))
+    lib.fa_set_mode(fb._lib.FA_MODE_BF16)
+    pinned_ptrs = []
+    if path == "ops":
+        ops, T = fb.CudaKernelOps, fb.tensor_from_numpy
+        q, k, v, do = (T(fill(np.empty((B, H, N, d), dtype=np.float32))) for _ in range(4))
+        km = T(mask) if mask is not None else None
+        fw = ops.flash_attention_causal_fw if causal else ops.flash_attention_fw
+        bw = ops.flash_attention_causal_bw if causal else ops.flash_attention_bw
+
+        def step():
+            O, m, l = fw(q, k, v, key_mask=km)
+            dQ, dK, dV = bw(q, k, v, O, do, m, l, key_mask=km)
+            return float(dQ._tensor._storage[0])  # the step's result is read on the host
+    else:
+        def pinned(count):
+            p = lib.fa_malloc_host(count * 4)
+            if not p:
+                raise MemoryError("pinned allocation failed")
+            pinned_ptrs.append(p)
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(count,))
+
+        A = {k_: pinned(n) for k_ in ("Q", "K", "V", "O", "dO", "dQ", "dK", "dV")}
+        S = {k_: pinned(r) for k_ in ("l", "m")}
+        for k_ in ("Q", "K", "V", "dO"):
+            fill(A[k_])
+        mptr = mask.ctypes.data_as(ctypes.c_void_p) if mask is not None else None
+
+        def step():
+            lib.launch_flashattention_forward_masked(A["Q"], A["K"], A["V"], A["O"], S["l"], S["m"], mptr, int(causal),
+                                                     B, H, N, d)
+            fb._lib.check(lib)
+            lib.launch_flashattention_backward_masked(A["Q"], A["K"], A["V"], A["O"], A["dQ"], A["dK"], A["dV"], A["dO"],
+                                                      S["l"], S["m"], mptr, int(causal), B, H, N, d)
+            fb._lib.check(lib)
+            return float(A["dQ"][0])
 
     step()
     barrier(dist)
@@ -422,20 +565,27 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, flops_step, steps, dist):
     for _ in range(steps):
         step()
     lib.fa_sync()
+    local_dt = time.perf_counter() - t0
     barrier(dist)
-    dt = reduce_max(dist, time.perf_counter() - t0)
+    dt = reduce_max(dist, local_dt)
     total = reduce_sum(dist, flops_step * steps)
     lib.fa_set_mode(fb._lib.FA_MODE_FP32)
-    for p, _ in list(bufs.values()) + list(stats.values()):
-        if p:
-            lib.fa_free_host(p)
-    h2d = (3 * n + 5 * n + 2 * r) * 4 + (mask.nbytes * 2 if mask is not None else 0)   # fwd: Q,K,V; bwd: Q,K,V,O,dO,m,l
-    d2h = (n + 2 * r + 3 * n) * 4
+    hits, miss = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib.fa_forward_cache_stats(ctypes.byref(hits), ctypes.byref(miss))
+    lib.fa_release_staging()
+    for p in pinned_ptrs:
+        lib.fa_free_host(p)
+    reuse = (hits.value - hits0.value) > 0
+    # bytes that cross PCIe per step: bf16 on the wire; the backward re-uses the forward's device tensors when cached
+    h2d = 3 * n * 2 + (n * 2 if reuse else (5 * n * 2 + 2 * r * 4)) + (mask.nbytes * 2 if mask is not None else 0)
+    d2h = n * 2 + 2 * r * 4 + 3 * n * 2
     return {"value": total / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": dt / steps * 1e3, "batch_per_gpu": B,
-            "path": "launch_flashattention_forward_masked + launch_flashattention_backward_masked (legacy C ABI, "
-                    "fp32 %s host buffers, FA_MODE_BF16), wall clock incl. H2D/D2H" % (
-                        "pageable" if os.environ.get("BENCH_E2E_PAGEABLE") == "1" else "pinned")}
+            "forward_tensors_reused_by_backward": bool(reuse),
+            "path": ("CudaKernelOps.flash_attention_fw/_bw(key_mask) on numpy-backed (pageable) fp32 tensors -> legacy C "
+                     "ABI, FA_MODE_BF16, bf16 on the wire" if path == "ops" else
+                     "launch_flashattention_{forward,backward}_masked by raw ctypes, fp32 page-locked host buffers, "
+                     "FA_MODE_BF16, bf16 on the wire") + "; wall clock incl. H2D/D2H"}
 
 
 if __name__ == "__main__":

@@ -66,13 +66,25 @@ enum { FA_DTYPE_F32 = 0, FA_DTYPE_BF16 = 1 };
 enum { FA_MODE_FP32 = 0, FA_MODE_BF16 = 1 };
 void fa_set_mode(int mode);
 int fa_get_mode(void);
-/* The legacy entry points are transfer-bound, so they cut the (batch, head) units into chunks of about
- * this many bytes of fp32 per tensor and overlap H2D of chunk c+1, the kernels of chunk c and D2H of
- * chunk c-1 on three streams (results are independent of the chunking).  Default 16 MiB (measured best of 4..64 on cfg4), or env
- * MINITORCH_FA_CHUNK_MB; 0 restores the default.  Caller buffers that are NOT page-locked (numpy storage) are staged
- * through a ring of pinned slots by up to 16 host threads (env MINITORCH_FA_COPY_THREADS) in 64 MiB chunks: 169 ms per
- * cfg4 step instead of the 511 ms of the driver's own pageable path (88 ms from pinned buffers). */
+/* The legacy entry points are transfer-bound, so they cut the (batch, head) units into chunks of about this many bytes of
+ * fp32 per tensor and overlap H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 on three streams (results are
+ * independent of the chunking).  Default 16 MiB for direct copies / 64 MiB for staged ones, or env MINITORCH_FA_CHUNK_MB;
+ * 0 restores the default.  Caller buffers that are NOT page-locked (numpy storage) are staged through a ring of pinned
+ * slots by a persistent pool of host threads (at most 16, env MINITORCH_FA_COPY_THREADS).  In FA_MODE_BF16 the wire format
+ * is bf16: the host threads narrow fp32 -> bf16 while staging and widen the results on the way back, halving the bytes
+ * on PCIe in both directions.
+ * Threading: the legacy entry points keep per-device state (streams, events, pinned rings) and must be called from one
+ * host thread at a time per process, like the reference's (single-threaded Python over ctypes). */
 void fa_set_legacy_chunk_bytes(size_t bytes);
+/* A forward call keeps its device copies of Q, K, V, O, m, l alive so that the matching backward call (same host pointers
+ * and shape, same sampled fingerprint of the contents) uploads only dO.  Bounded by this budget (default 4096 MiB, env
+ * MINITORCH_FA_KEEP_FWD_MB; 0 disables): oldest entries are dropped first, a backward consumes its entry. */
+void fa_set_keep_forward_mb(long long mb);
+void fa_forward_cache_stats(unsigned long long* hits, unsigned long long* misses);
+/* Times a pinned staging ring could not be allocated and a call fell back to direct (slow, pageable) copies. */
+unsigned long long fa_staging_fallbacks(void);
+/* Release the pinned staging rings and the cached forward tensors of the current device. */
+int fa_release_staging(void);
 
 /* Legacy ABI -- identical to the reference's
  *   src/flashattention_kernel.cu:259 launch_flashattention_forward
@@ -106,7 +118,9 @@ void launch_flashattention_backward_masked(float* Q, float* K, float* V, float* 
  * what MultiHeadAttention.project_to_query_key_value produces before its permute,
  * minitorch/modules_transfomer.py:87-100 -- is stride_b=N*nh*d, stride_h=d, stride_n=nh*d.
  * kv_len: optional int32[B] (keys >= kv_len[b] are padding); key_mask: optional fp32 (B,N)
- * additive mask.  Returns FA_OK or an error code (message via fa_last_error()). */
+ * additive mask.  Returns FA_OK or an error code (message via fa_last_error()).
+ * Workspaces (LSE / D vectors, the fp32 dQ accumulator) are allocated stream-ordered on `stream` from the device's
+ * default memory pool, so calls in flight on different streams are independent. */
 typedef struct {
   int B, H, N, d;
   int dtype;      /* FA_DTYPE_* */

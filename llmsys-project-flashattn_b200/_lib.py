@@ -69,6 +69,10 @@ SYMBOLS = {
         "fa_set_mode": (None, [c_int]),
         "fa_get_mode": (c_int, []),
         "fa_set_legacy_chunk_bytes": (None, [c_size_t]),
+        "fa_set_keep_forward_mb": (None, [c_longlong]),
+        "fa_forward_cache_stats": (None, [POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),
+        "fa_staging_fallbacks": (ctypes.c_ulonglong, []),
+        "fa_release_staging": (c_int, []),
         "launch_flashattention_forward": (None, _HOST4),
         "launch_flashattention_forward_causal": (None, _HOST4),
         "launch_flashattention_backward": (None, _HOST4B),

@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(640, 1)
       // Warp 18 + hh serves the warpgroups (., hh): staging box hh receives columns [D/2*hh + 32*c2, +32) of
       // dQ_it from warpgroup (it & 1, hh); one lane turns each fill into a TMA add-reduction and hands the
       // box to its next user once the TMA has read it.  The two halves never wait for each other.
+#ifndef FA_EXP_NODRAIN
       if (lane == 0) {
         constexpr int PER_WG = D / 64;   // 32-column boxes per warpgroup and iteration
         const int hh = warp - 18;
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(640, 1)
         }
         tma_store_wait_all<0>();
       }
+#endif
       __syncwarp();
     }
   } else {
@@ -462,7 +464,11 @@ __global__ void __launch_bounds__(640, 1)
         const bool masked = !(all_keys_ok && !diag);
 #pragma unroll
         for (int c4 = 0; c4 < 16; ++c4) {
+#ifdef FA_EXP_NOSTATS   // timing-only experiment: no shared-memory loads of the row statistics
+          const float4 l4 = make_float4(p.scale, p.scale, p.scale, p.scale);
+#else
           const float4 l4 = *reinterpret_cast<const float4*>(nlse + 4 * c4);
+#endif
           float x0, x1, x2, x3;
           f32x2_unpack(fma_f32x2(f32x2(s[4 * c4], s[4 * c4 + 1]), sc2, f32x2(l4.x, l4.y)), x0, x1);
           f32x2_unpack(fma_f32x2(f32x2(s[4 * c4 + 2], s[4 * c4 + 3]), sc2, f32x2(l4.z, l4.w)), x2, x3);
@@ -499,8 +505,12 @@ __global__ void __launch_bounds__(640, 1)
         const uint32_t(&u)[16] = ua[c & 1];
 #pragma unroll
         for (int v8 = 0; v8 < 2; ++v8) {   // 8 queries -> one 16-byte piece
+#ifdef FA_EXP_NOSTATS
+          const float4 da = make_float4(p.scale, p.scale, p.scale, p.scale), db = da;
+#else
           const float4 da = *reinterpret_cast<const float4*>(dv + 16 * c + 8 * v8);
           const float4 db = *reinterpret_cast<const float4*>(dv + 16 * c + 8 * v8 + 4);
+#endif
           uint4 o;
           o.x = bf16x2_mul(pk[8 * c + 4 * v8 + 0], pack_bf16x2(__uint_as_float(u[8 * v8 + 0]) - da.x,
                                                                __uint_as_float(u[8 * v8 + 1]) - da.y));
@@ -531,6 +541,7 @@ __global__ void __launch_bounds__(640, 1)
       tc_fence_before();
       mbar_arrive(&dq_free[g]);          // T_dP may be overwritten by dP(it+1)
       FA_TR(14)
+#ifndef FA_EXP_NODRAIN   // (timing-only experiment: dQ is read out of TMEM and dropped)
 #pragma unroll
       for (int c2 = 0; c2 < D / 64; ++c2) {
         // use number u of staging box hh by THIS warpgroup; group 0's very first use finds the box free
@@ -544,6 +555,9 @@ __global__ void __launch_bounds__(640, 1)
         fence_proxy_async_smem();
         mbar_arrive(&stg_full[hh]);
       }
+#else
+      asm volatile("" ::"r"(dq[0][0]), "r"(dq[D / 64 - 1][31]));
+#endif
       FA_TR(15)
     }
 

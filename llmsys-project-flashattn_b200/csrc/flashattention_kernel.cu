@@ -10,7 +10,6 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
-#include <thread>
 #include <vector>
 
 #include "host_common.cuh"
@@ -146,8 +145,15 @@ static int bwd_simt(const fa_attn_desc* a, const void* Q, const void* K, const v
                     const float* m, const float* l, void* dQ, void* dK, void* dV, cudaStream_t st) {
   AttnParams p = make_params(a);
   const long long rows = (long long)p.B * p.H * p.N;
-  float* ws = static_cast<float*>(g_pool.get(12, sizeof(float) * 2 * rows));
+  // workspace is stream-ordered (taken from / returned to the cached default pool on `st`): calls in flight on
+  // different streams never share it
+  float* ws = static_cast<float*>(pool_alloc(sizeof(float) * 2 * rows, st));
   if (!ws) return set_error(FA_ERR_CUDA, "flash bwd: workspace allocation failed");
+  struct Release {
+    void* p;
+    cudaStream_t st;
+    ~Release() { cudaFreeAsync(p, st); }
+  } release{ws, st};
   float *Dv = ws, *LSE = ws + rows;
   int rc = bwd_prep<T>(p, O, dO, m, l, Dv, LSE, st);
   if (rc != FA_OK) return rc;
@@ -257,8 +263,17 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   const int Npad = ((a->N + 127) / 128) * 128;
   const size_t rows_pad = (size_t)a->B * a->H * Npad;
   const size_t nacc = (size_t)a->B * a->H * a->N * a->d;
-  float* ws = static_cast<float*>(g_pool.get(13, sizeof(float) * 2 * rows_pad));
-  float* acc = static_cast<float*>(g_pool.get(14, sizeof(float) * nacc));
+  // stream-ordered workspace (see bwd_simt): LSE / D vectors and the fp32 dQ accumulator
+  float* ws = static_cast<float*>(pool_alloc(sizeof(float) * 2 * rows_pad, st));
+  float* acc = static_cast<float*>(pool_alloc(sizeof(float) * nacc, st));
+  struct Release {
+    void *a, *b;
+    cudaStream_t st;
+    ~Release() {
+      if (a) cudaFreeAsync(a, st);
+      if (b) cudaFreeAsync(b, st);
+    }
+  } release{ws, acc, st};
   if (!ws || !acc) return set_error(FA_ERR_CUDA, "flash bwd: workspace allocation failed");
   float *lse2 = ws, *dvec = ws + rows_pad;
   {
@@ -430,462 +445,50 @@ int fa_flash_bwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const 
   return bwd_simt<__nv_bfloat16>(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
 }
 
+}  // extern "C" (device-pointer API above; the legacy host-pointer ABI follows)
+
+namespace fa {
+static bool tc_head_dim(int d) { return d == 64 || d == 128; }
+static int fwd_tc_bf16(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, float* m, float* l,
+                       cudaStream_t st) {
+  Strides s = resolve_strides(a);
+  return fwd_tc<__nv_bfloat16>(a, Q, K, V, O, s.sb, s.sh, s.sn, m, l, st);
+}
+}  // namespace fa
+#include "legacy_pipeline.cuh"
+
+extern "C" {
+
 // ---------------------------------------------------------------------------------------------
-// Legacy host-pointer ABI.  fp32 host buffers in, fp32 host buffers out.
+// Legacy host-pointer ABI.  fp32 host buffers in, fp32 host buffers out (legacy_pipeline.cuh).
 // ---------------------------------------------------------------------------------------------
-// A LightSeq-style padding mask is "0 on the first kv_len[b] keys, a huge negative number after"
-// (kernel_tests/test_softmax_fw.py:44-45 uses -1e8).  When every row of the host mask has that
-// shape (tail <= -1e6, at least one valid key) the kernels can skip whole KV tiles through
-// kv_len[] instead of adding the mask element by element; otherwise the generic path is used.
-static bool mask_to_kv_len(const float* key_mask, int B, int N, int* kv_len_out) {
-  for (int b = 0; b < B; ++b) {
-    const float* r = key_mask + (size_t)b * N;
-    int n = 0;
-    while (n < N && r[n] == 0.0f) ++n;
-    if (n == 0) return false;
-    for (int j = n; j < N; ++j)
-      if (!(r[j] <= -1e6f)) return false;
-    kv_len_out[b] = n;
-  }
-  return true;
-}
-// Upload either kv_len[] (fast path) or the additive mask into the descriptor.
-static int stage_mask(fa_attn_desc* a, const float* key_mask, int slot) {
-  if (!key_mask) return FA_OK;
-  const size_t bytes = (size_t)a->B * a->N * 4 + (size_t)a->B * 4 + 16;
-  char* d = static_cast<char*>(g_pool.get(slot, bytes));
-  if (!d) return set_error(FA_ERR_CUDA, "mask staging allocation failed");
-  static int* h_kv = nullptr;
-  static int h_cap = 0;
-  if (h_cap < a->B) {
-    free(h_kv);
-    h_kv = static_cast<int*>(malloc(sizeof(int) * a->B));
-    h_cap = a->B;
-  }
-  if (mask_to_kv_len(key_mask, a->B, a->N, h_kv)) {
-    FA_CUDA_CHECK(cudaMemcpyAsync(d, h_kv, (size_t)a->B * 4, cudaMemcpyHostToDevice, 0));
-    FA_CUDA_CHECK(cudaStreamSynchronize(0));  // h_kv is reused by the next call
-    a->kv_len = reinterpret_cast<const int*>(d);
-  } else {
-    char* dm = d + (((size_t)a->B * 4 + 15) & ~size_t(15));
-    FA_CUDA_CHECK(cudaMemcpyAsync(dm, key_mask, (size_t)a->B * a->N * 4, cudaMemcpyHostToDevice, 0));
-    a->key_mask = reinterpret_cast<const float*>(dm);
-  }
-  return FA_OK;
-}
-
-// The legacy calls are transfer-bound (cfg4: 6.4 GB over PCIe per fwd+bwd step against 7 ms of kernels), so
-// the (batch, head) units -- independent attention problems -- are cut into chunks that flow through three
-// streams: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 run concurrently (both copy directions
-// of the link are busy at once).  A chunk never straddles a batch, so kv_len / the key mask index by batch.
-struct LegacyPipe {
-  cudaStream_t in = nullptr, comp = nullptr, out = nullptr;
-  cudaEvent_t ev_in[256] = {}, ev_comp[256] = {};
-  int dev = -1;
-  int nev = 0;
-  int init() {
-    int d = 0;
-    FA_CUDA_CHECK(cudaGetDevice(&d));
-    if (dev == d && in) return FA_OK;
-    if (in) {  // device changed: the old device's streams stay alive (tiny), make new ones
-      in = comp = out = nullptr;
-      nev = 0;
-    }
-    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
-    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
-    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
-    dev = d;
-    return FA_OK;
-  }
-  int events(int n) {
-    if (n > 256) return set_error(FA_ERR_INVALID, "legacy pipeline: too many chunks (%d)", n);
-    for (; nev < n; ++nev) {
-      FA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in[nev], cudaEventDisableTiming));
-      FA_CUDA_CHECK(cudaEventCreateWithFlags(&ev_comp[nev], cudaEventDisableTiming));
-    }
-    return FA_OK;
-  }
-  int drain() {
-    cudaError_t e1 = cudaStreamSynchronize(in), e2 = cudaStreamSynchronize(comp), e3 = cudaStreamSynchronize(out);
-    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
-    if (e != cudaSuccess) return set_error(FA_ERR_CUDA, "legacy pipeline: %s", cudaGetErrorString(e));
-    return FA_OK;
-  }
-};
-static LegacyPipe g_pipe;
-
-struct Chunk {
-  int b, nb, h0, hc;   // batches [b, b+nb) x heads [h0, h0+hc); nb > 1 only with all heads (contiguous slab)
-};
-// About g_chunk_bytes of fp32 per tensor and chunk, at most `cap` chunks: whole batches when a batch fits in a
-// chunk (small problems become ONE chunk: every extra chunk costs ~10 driver calls), otherwise groups of heads
-// inside one batch.
-static size_t g_chunk_bytes = 0;  // 0 = unresolved: env MINITORCH_FA_CHUNK_MB or 16 MiB
-static bool g_chunk_explicit = false;
-// `pageable`: the caller's buffers are not page-locked -> chunks are staged by host threads, and bigger chunks
-// (64 MiB measured best: 170 ms vs 270 ms per cfg4 step at 16 MiB) amortise the per-chunk thread fork/join.
-static int plan_chunks(int B, int nh, int N, int d, Chunk* out, int cap, bool pageable = false) {
-  if (!g_chunk_bytes) {
-    const char* e = getenv("MINITORCH_FA_CHUNK_MB");
-    const long mb = e ? atol(e) : 16;
-    g_chunk_explicit = e != nullptr;
-    g_chunk_bytes = (size_t)(mb > 0 ? mb : 16) << 20;
-  }
-  const size_t chunk_bytes = (pageable && !g_chunk_explicit) ? ((size_t)64 << 20) : g_chunk_bytes;
-  const size_t head_bytes = (size_t)N * d * 4;
-  const size_t batch_bytes = head_bytes * nh;
-  int hc = (int)(chunk_bytes / head_bytes);
-  if (hc < 1) hc = 1;
-  if (hc > nh) hc = nh;
-  while (hc < nh && (size_t)B * ((nh + hc - 1) / hc) > (size_t)cap) ++hc;
-  int n = 0;
-  if (hc == nh) {
-    size_t nb = batch_bytes <= chunk_bytes ? chunk_bytes / batch_bytes : 1;
-    if (nb < 1) nb = 1;
-    while (((size_t)B + nb - 1) / nb > (size_t)cap) ++nb;
-    for (int b = 0; b < B; b += (int)nb) out[n++] = Chunk{b, (B - b < (int)nb) ? B - b : (int)nb, 0, nh};
-    return n;
-  }
-  for (int b = 0; b < B; ++b)
-    for (int h0 = 0; h0 < nh; h0 += hc) out[n++] = Chunk{b, 1, h0, (nh - h0 < hc) ? nh - h0 : hc};
-  return n;
-}
-
-// ---- pageable host buffers (what a numpy-backed minitorch tensor hands over) -------------------------------------
-// cudaMemcpyAsync from / to pageable memory is staged by the driver on one thread (~12 GB/s measured: 511 ms per cfg4
-// step against 88 ms from pinned buffers) and D2H into pageable memory blocks the caller.  When a caller's buffer is
-// not page-locked the chunks therefore go through a small ring of pinned staging slots owned by the library, filled /
-// emptied by a few host threads while the previous chunk is on the wire.
-static bool is_pageable(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return true;
-  }
-  return a.type == cudaMemoryTypeUnregistered;
-}
-static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  static const int nt = [] {
-    const char* e = getenv("MINITORCH_FA_COPY_THREADS");
-    int n = e ? atoi(e) : 0;
-    if (n <= 0) {
-      n = (int)std::thread::hardware_concurrency();
-      n = n > 16 ? 16 : (n < 1 ? 1 : n);
-    }
-    return n;
-  }();
-  if (bytes < ((size_t)2 << 20) || nt == 1) {
-    memcpy(dst, src, bytes);
-    return;
-  }
-  const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
-  std::vector<std::thread> th;
-  for (int i = 1; i < nt; ++i) {
-    const size_t off = (size_t)i * per;
-    if (off >= bytes) break;
-    const size_t len = (bytes - off < per) ? bytes - off : per;
-    th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
-  }
-  memcpy(dst, src, per < bytes ? per : bytes);
-  for (auto& t : th) t.join();
-}
-struct StageRing {
-  static constexpr int S = 3;        // slots in flight
-  int T = 0;                         // tensors per slot (7 inputs / 3 outputs per chunk at most)
-  char* base = nullptr;
-  size_t slot_bytes = 0;
-  cudaEvent_t ev[S] = {};
-  bool used[S] = {};
-  struct Pending {
-    void* dst;
-    const void* src;
-    size_t bytes;
-  };
-  std::vector<Pending> pending[S];
-  bool ensure(size_t bytes, int ntens) {
-    if (bytes <= slot_bytes && ntens <= T) return true;
-    if (base) cudaFreeHost(base);
-    base = nullptr, slot_bytes = 0;
-    if (ntens > T) T = ntens;
-    if (cudaMallocHost(reinterpret_cast<void**>(&base), (size_t)S * T * bytes) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    slot_bytes = bytes;
-    for (int i = 0; i < S; ++i) {
-      if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
-      used[i] = false;
-      pending[i].clear();
-    }
-    return true;
-  }
-  void* slot(int s, int t) { return base + ((size_t)s * T + t) * slot_bytes; }
-  // input side: slot s may be overwritten once the H2D copies that last read it have finished
-  void acquire_in(int s) {
-    if (used[s]) cudaEventSynchronize(ev[s]);
-  }
-  void release_in(int s, cudaStream_t st) {
-    cudaEventRecord(ev[s], st);
-    used[s] = true;
-  }
-  // output side: copy a finished slot into the caller's buffers
-  void drain_out(int s) {
-    if (!used[s]) return;
-    cudaEventSynchronize(ev[s]);
-    for (const Pending& p : pending[s]) parallel_memcpy(p.dst, p.src, p.bytes);
-    pending[s].clear();
-    used[s] = false;
-  }
-};
-static StageRing g_ring_in, g_ring_out;
-
-static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, float* m, const float* key_mask,
-                           int causal, int B, int nh, int N, int d) {
-  clear_error();
-  fa_attn_desc a{};
-  a.B = B, a.H = nh, a.N = N, a.d = d, a.causal = causal;
-  a.dtype = FA_DTYPE_F32;
-  if (validate(&a, "launch_flashattention_forward")) return;
-  const size_t n = (size_t)B * nh * N * d, r = (size_t)B * nh * N;
-  float* dQ_ = static_cast<float*>(g_pool.get(0, n * 4));
-  float* dK_ = static_cast<float*>(g_pool.get(1, n * 4));
-  float* dV_ = static_cast<float*>(g_pool.get(2, n * 4));
-  float* dO_ = static_cast<float*>(g_pool.get(3, n * 4));
-  float* dml = static_cast<float*>(g_pool.get(4, 2 * r * 4));
-  if (!dQ_ || !dK_ || !dV_ || !dO_ || !dml) {
-    set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed (%zu bytes per tensor)", n * 4);
-    return;
-  }
-  float *dm = dml, *dl = dml + r;
-  const bool tc = current_mode() == FA_MODE_BF16 && (d == 64 || d == 128);
-  __nv_bfloat16 *bq = nullptr, *bk = nullptr, *bv = nullptr;
-  if (tc) {  // round the operands to bf16 on device; the kernel writes fp32 O directly
-    bq = static_cast<__nv_bfloat16*>(g_pool.get(5, n * 2));
-    bk = static_cast<__nv_bfloat16*>(g_pool.get(6, n * 2));
-    bv = static_cast<__nv_bfloat16*>(g_pool.get(7, n * 2));
-    if (!bq || !bk || !bv) {
-      set_error(FA_ERR_CUDA, "launch_flashattention_forward: bf16 staging allocation failed");
-      return;
-    }
-  }
-  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
-  if (cudaStreamSynchronize(0) != cudaSuccess) {
-    set_error(FA_ERR_CUDA, "launch_flashattention_forward: mask upload failed");
-    return;
-  }
-  // pageable caller buffers of a non-trivial size go through the pinned staging rings
-  bool staged = n * 4 >= ((size_t)256 << 10) && (is_pageable(Q) || is_pageable(K) || is_pageable(V) || is_pageable(O));
-  static Chunk chunks[256];
-  const int nc = plan_chunks(B, nh, N, d, chunks, 256, staged);
-  LegacyPipe& P = g_pipe;
-  if (P.init() != FA_OK || P.events(nc) != FA_OK) return;
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) {
-    if (e == cudaSuccess) e = x;
-  };
-  size_t max_cn = 0;
-  for (int c = 0; c < nc; ++c) {
-    const size_t cn = (size_t)chunks[c].nb * chunks[c].hc * N * d;
-    if (cn > max_cn) max_cn = cn;
-  }
-  if (staged && !(g_ring_in.ensure(max_cn * 4, 7) && g_ring_out.ensure(max_cn * 4, 3))) staged = false;
-  constexpr int RS = StageRing::S;
-  auto h2d = [&](int c, int t, float* dst, const float* src, size_t count) {
-    if (!staged) return step(cudaMemcpyAsync(dst, src, count * 4, cudaMemcpyHostToDevice, P.in));
-    void* st = g_ring_in.slot(c % RS, t);
-    parallel_memcpy(st, src, count * 4);
-    step(cudaMemcpyAsync(dst, st, count * 4, cudaMemcpyHostToDevice, P.in));
-  };
-  auto d2h = [&](int c, int t, float* dst, const float* src, size_t count) {
-    if (!staged) return step(cudaMemcpyAsync(dst, src, count * 4, cudaMemcpyDeviceToHost, P.out));
-    void* st = g_ring_out.slot(c % RS, t);
-    step(cudaMemcpyAsync(st, src, count * 4, cudaMemcpyDeviceToHost, P.out));
-    g_ring_out.pending[c % RS].push_back({dst, st, count * 4});
-  };
-  int rc = FA_OK, issued = 0, drained = 0;
-  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
-    const Chunk& ck = chunks[c];
-    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
-    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
-    if (staged) g_ring_in.acquire_in(c % RS);
-    h2d(c, 0, dQ_ + off, Q + off, cn);
-    h2d(c, 1, dK_ + off, K + off, cn);
-    h2d(c, 2, dV_ + off, V + off, cn);
-    if (staged) g_ring_in.release_in(c % RS, P.in);
-    step(cudaEventRecord(P.ev_in[c], P.in));
-    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
-    fa_attn_desc ca = a;
-    ca.B = ck.nb, ca.H = ck.hc;
-    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
-    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
-    fa_stream_t cs = reinterpret_cast<fa_stream_t>(P.comp);
-    if (tc) {
-      if (fa_cast_f32_to_bf16_dev(dQ_ + off, bq + off, cn, cs) || fa_cast_f32_to_bf16_dev(dK_ + off, bk + off, cn, cs) ||
-          fa_cast_f32_to_bf16_dev(dV_ + off, bv + off, cn, cs)) {
-        rc = fa_last_status();
-        break;
-      }
-      ca.dtype = FA_DTYPE_BF16;
-      rc = fwd_tc<float>(&ca, bq + off, bk + off, bv + off, dO_ + off, (long long)ck.hc * N * d, (long long)N * d, d,
-                         dm + roff, dl + roff, P.comp);
-    } else {
-      rc = fa_flash_fwd_dev(&ca, dQ_ + off, dK_ + off, dV_ + off, dO_ + off, dm + roff, dl + roff, cs);
-    }
-    if (rc != FA_OK) break;
-    step(cudaEventRecord(P.ev_comp[c], P.comp));
-    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
-    d2h(c, 0, O + off, dO_ + off, cn);
-    d2h(c, 1, m + roff, dm + roff, cr);
-    d2h(c, 2, l + roff, dl + roff, cr);
-    if (staged) {
-      g_ring_out.release_in(c % RS, P.out);               // (same event bookkeeping: "slot c is complete after this")
-      ++issued;
-      while (issued - drained > RS - 1) g_ring_out.drain_out(drained++ % RS);
-    }
-  }
-  if (staged) {
-    while (drained < issued) g_ring_out.drain_out(drained++ % RS);
-    for (int i = 0; i < RS; ++i) g_ring_out.pending[i].clear(), g_ring_out.used[i] = false, g_ring_in.used[i] = false;
-  }
-  // always drain: the caller owns the host buffers and may free them as soon as we return
-  const int saved = fa_last_status();
-  char saved_msg[512];
-  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
-  saved_msg[sizeof(saved_msg) - 1] = 0;
-  const int drc = P.drain();
-  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
-  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_forward: %s", cudaGetErrorString(e));
-  (void)drc;
-}
-
-static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV, float* dO,
-                            float* l, float* m, const float* key_mask, int causal, int B, int nh, int N, int d) {
-  clear_error();
-  fa_attn_desc a{};
-  a.B = B, a.H = nh, a.N = N, a.d = d, a.causal = causal;
-  a.dtype = FA_DTYPE_F32;
-  if (validate(&a, "launch_flashattention_backward")) return;
-  const size_t n = (size_t)B * nh * N * d, r = (size_t)B * nh * N;
-  float* buf[8];
-  for (int i = 0; i < 8; ++i) {
-    buf[i] = static_cast<float*>(g_pool.get(i, n * 4));
-    if (!buf[i]) {
-      set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed (%zu bytes per tensor)", n * 4);
-      return;
-    }
-  }
-  float* dml = static_cast<float*>(g_pool.get(9, 2 * r * 4));
-  if (!dml) {
-    set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed");
-    return;
-  }
-  float *dm = dml, *dl = dml + r;
-  const bool tc = current_mode() == FA_MODE_BF16 && (d == 64 || d == 128);
-  // bf16 mode: round the fp32 operands to bf16 on device, run the bf16 backward, widen the gradients
-  // back to fp32 into the fp32 staging buffers.
-  __nv_bfloat16* hb[8] = {};
-  if (tc)
-    for (int i = 0; i < 8; ++i) {
-      hb[i] = static_cast<__nv_bfloat16*>(g_pool.get(16 + i, n * 2));
-      if (!hb[i]) {
-        set_error(FA_ERR_CUDA, "launch_flashattention_backward: bf16 staging allocation failed");
-        return;
-      }
-    }
-  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
-  if (cudaStreamSynchronize(0) != cudaSuccess) {
-    set_error(FA_ERR_CUDA, "launch_flashattention_backward: mask upload failed");
-    return;
-  }
-  float* const host_in[5] = {Q, K, V, O, dO};
-  float* const host_out[3] = {dQ, dK, dV};
-  bool staged = n * 4 >= ((size_t)256 << 10);
-  if (staged) {
-    bool any = is_pageable(dQ) || is_pageable(dK) || is_pageable(dV);
-    for (int i = 0; i < 5; ++i) any = any || is_pageable(host_in[i]);
-    staged = any;
-  }
-  static Chunk chunks[256];
-  const int nc = plan_chunks(B, nh, N, d, chunks, 256, staged);
-  LegacyPipe& P = g_pipe;
-  if (P.init() != FA_OK || P.events(nc) != FA_OK) return;
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) {
-    if (e == cudaSuccess) e = x;
-  };
-  size_t max_cn = 0;
-  for (int c = 0; c < nc; ++c) {
-    const size_t cn = (size_t)chunks[c].nb * chunks[c].hc * N * d;
-    if (cn > max_cn) max_cn = cn;
-  }
-  if (staged) staged = g_ring_in.ensure(max_cn * 4, 7) && g_ring_out.ensure(max_cn * 4, 3);
-  constexpr int RS = StageRing::S;
-  auto h2d = [&](int c, int t, float* dst, const float* src, size_t count) {
-    if (!staged) return step(cudaMemcpyAsync(dst, src, count * 4, cudaMemcpyHostToDevice, P.in));
-    void* st = g_ring_in.slot(c % RS, t);
-    parallel_memcpy(st, src, count * 4);
-    step(cudaMemcpyAsync(dst, st, count * 4, cudaMemcpyHostToDevice, P.in));
-  };
-  auto d2h = [&](int c, int t, float* dst, const float* src, size_t count) {
-    if (!staged) return step(cudaMemcpyAsync(dst, src, count * 4, cudaMemcpyDeviceToHost, P.out));
-    void* st = g_ring_out.slot(c % RS, t);
-    step(cudaMemcpyAsync(st, src, count * 4, cudaMemcpyDeviceToHost, P.out));
-    g_ring_out.pending[c % RS].push_back({dst, st, count * 4});
-  };
-  int rc = FA_OK, issued = 0, drained = 0;
-  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
-    const Chunk& ck = chunks[c];
-    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
-    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
-    if (staged) g_ring_in.acquire_in(c % RS);
-    for (int i = 0; i < 5; ++i) h2d(c, i, buf[i] + off, host_in[i] + off, cn);
-    h2d(c, 5, dm + roff, m + roff, cr);
-    h2d(c, 6, dl + roff, l + roff, cr);
-    if (staged) g_ring_in.release_in(c % RS, P.in);
-    step(cudaEventRecord(P.ev_in[c], P.in));
-    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
-    fa_attn_desc ca = a;
-    ca.B = ck.nb, ca.H = ck.hc;
-    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
-    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
-    fa_stream_t cs = reinterpret_cast<fa_stream_t>(P.comp);
-    if (tc) {
-      for (int i = 0; i < 5 && rc == FA_OK; ++i) rc = fa_cast_f32_to_bf16_dev(buf[i] + off, hb[i] + off, cn, cs);
-      ca.dtype = FA_DTYPE_BF16;
-      if (rc == FA_OK)
-        rc = fa_flash_bwd_dev(&ca, hb[0] + off, hb[1] + off, hb[2] + off, hb[3] + off, hb[4] + off, dm + roff,
-                              dl + roff, hb[5] + off, hb[6] + off, hb[7] + off, cs);
-      for (int i = 0; i < 3 && rc == FA_OK; ++i) rc = fa_cast_bf16_to_f32_dev(hb[5 + i] + off, buf[5 + i] + off, cn, cs);
-    } else {
-      rc = fa_flash_bwd_dev(&ca, buf[0] + off, buf[1] + off, buf[2] + off, buf[3] + off, buf[4] + off, dm + roff,
-                            dl + roff, buf[5] + off, buf[6] + off, buf[7] + off, cs);
-    }
-    if (rc != FA_OK) break;
-    step(cudaEventRecord(P.ev_comp[c], P.comp));
-    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
-    for (int i = 0; i < 3; ++i) d2h(c, i, host_out[i] + off, buf[5 + i] + off, cn);
-    if (staged) {
-      g_ring_out.release_in(c % RS, P.out);
-      ++issued;
-      while (issued - drained > RS - 1) g_ring_out.drain_out(drained++ % RS);
-    }
-  }
-  if (staged) {
-    while (drained < issued) g_ring_out.drain_out(drained++ % RS);
-    for (int i = 0; i < RS; ++i) g_ring_out.pending[i].clear(), g_ring_out.used[i] = false, g_ring_in.used[i] = false;
-  }
-  const int saved = fa_last_status();
-  char saved_msg[512];
-  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
-  saved_msg[sizeof(saved_msg) - 1] = 0;
-  P.drain();
-  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
-  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
-}
-
 void fa_set_legacy_chunk_bytes(size_t bytes) {
   g_chunk_bytes = bytes ? bytes : ((size_t)16 << 20);
   g_chunk_explicit = bytes != 0;
+}
+void fa_set_keep_forward_mb(long long mb) { g_keep_budget = (mb < 0 ? 0 : mb) << 20; }
+void fa_forward_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  if (hits) *hits = g_fwd_hits;
+  if (misses) *misses = g_fwd_misses;
+}
+unsigned long long fa_staging_fallbacks(void) { return g_staging_fallbacks; }
+// Gives back what the legacy entry points hold between calls on the current device: the pinned staging rings and the
+// device copies of forward calls that are still waiting for their backward.
+int fa_release_staging(void) {
+  clear_error();
+  int dev = 0;
+  FA_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= ScratchPool::kMaxDev) return FA_OK;
+  DevPipe& P = g_pipes[dev];
+  if (P.ready) {
+    cudaError_t e = P.drain();
+    if (e != cudaSuccess) return set_error(FA_ERR_CUDA, "fa_release_staging: %s", cudaGetErrorString(e));
+  }
+  P.rin.release();
+  P.rout.release();
+  drop_cached_forwards(dev, nullptr);
+  FA_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+  return FA_OK;
 }
 void launch_flashattention_forward(float* Q, float* K, float* V, float* O, float* l, float* m, int B, int nh, int N,
                                    int d) {

@@ -64,6 +64,31 @@ struct ScratchPool {
 };
 static ScratchPool g_pool;
 
+// Stream-ordered allocation from the device's default memory pool.  The release threshold is raised once per device so
+// that freed blocks stay cached in the pool: a workspace taken and returned on every call costs no driver round trip,
+// and two calls in flight on different streams can never share a buffer (which the grow-only slots above cannot promise).
+inline void tune_default_pool() {
+  static bool tuned[ScratchPool::kMaxDev] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= ScratchPool::kMaxDev || tuned[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  tuned[dev] = true;
+}
+inline void* pool_alloc(size_t bytes, cudaStream_t st) {
+  tune_default_pool();
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, bytes ? bytes : 16, st) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
 static unsigned long long g_launches = 0;
 inline void count_launch(int n = 1) { g_launches += static_cast<unsigned long long>(n); }
@@ -111,23 +136,8 @@ void* fa_malloc_host(size_t bytes) {
 // cached): what a device-resident tensor library allocates its per-op outputs from.
 void* fa_malloc_async(size_t bytes, fa_stream_t stream) {
   fa::clear_error();
-  static bool tuned[fa::ScratchPool::kMaxDev] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < fa::ScratchPool::kMaxDev && !tuned[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    tuned[dev] = true;
-  }
-  void* p = nullptr;
-  cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, reinterpret_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) {
-    fa::set_error(FA_ERR_CUDA, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    return nullptr;
-  }
+  void* p = fa::pool_alloc(bytes, reinterpret_cast<cudaStream_t>(stream));
+  if (!p) fa::set_error(FA_ERR_CUDA, "cudaMallocAsync(%zu) failed", bytes);
   return p;
 }
 int fa_free_async(void* p, fa_stream_t stream) {

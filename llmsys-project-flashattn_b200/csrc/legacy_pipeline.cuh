@@ -1,0 +1,743 @@
+// Host side of the legacy (reference-ABI) flash-attention entry points: fp32 HOST buffers in, fp32 HOST buffers out
+// (reference: src/flashattention_kernel.cu:259-326, :352-436, :694-757, :761-845 -- 6 cudaMalloc + 5-6 H2D + kernel +
+// 3 D2H + 6 cudaFree per call).  The calls are transfer-bound (cfg4: 5.9 ms of kernels against gigabytes over PCIe),
+// so this file is about moving as few bytes as possible and keeping both directions of the link busy:
+//   * the independent (batch, head) units are cut into chunks that flow through three streams -- H2D of chunk c+1,
+//     the kernels of chunk c and D2H of chunk c-1 run concurrently (one cudaMemcpyAsync per tensor and chunk);
+//   * in bf16 mode the wire format is bf16: host threads narrow fp32 -> bf16 while they copy a chunk into a pinned
+//     staging slot (a pageable numpy buffer has to be copied once anyway) and widen bf16 -> fp32 on the way back,
+//     which halves the bytes on the link in both directions;
+//   * the device copies of Q, K, V, O, m, l made by a forward call stay alive (bounded LRU, validated by host pointer,
+//     shape and a sampled fingerprint of the contents) so the matching backward call uploads only dO;
+//   * all per-device state (streams, events, pinned rings) is indexed by device, created once and reused.
+// Included by flashattention_kernel.cu only.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace fa {
+
+// ------------------------------------------------------------------------------------------------ host worker pool
+// A few persistent threads that copy / convert chunks between caller memory and the pinned staging slots.  Created
+// once (a failed thread creation leaves a smaller pool, in the worst case the caller's own thread: nothing throws
+// across the C ABI); idle workers sleep on a condition variable.
+class HostWorkers {
+ public:
+  static HostWorkers& get() {
+    static HostWorkers* w = new HostWorkers();   // intentionally leaked: no destructor races at process exit
+    return *w;
+  }
+  int threads() const { return static_cast<int>(workers_.size()) + 1; }
+  // fn(i) for every i in [0, n): pieces are handed out dynamically to the workers and the calling thread.
+  void run(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    if (n == 1 || workers_.empty()) {
+      for (int i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0);
+      pending_ = n;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  HostWorkers() {
+    const char* e = getenv("MINITORCH_FA_COPY_THREADS");
+    int n = e ? atoi(e) : 0;
+    if (n <= 0) {
+      n = static_cast<int>(std::thread::hardware_concurrency());
+      n = n > 16 ? 16 : (n < 1 ? 1 : n);
+    }
+    for (int i = 1; i < n; ++i) {
+      try {
+        workers_.emplace_back([this] { loop(); });
+      } catch (...) {
+        break;   // ulimit -u / cgroup pids limit: carry on with the threads we have
+      }
+    }
+    for (auto& t : workers_) t.detach();
+  }
+  void work() {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) break;
+      (*fn_)(i);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (!fn_) continue;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_ = 0, pending_ = 0;
+  std::atomic<int> next_{0};
+  unsigned long long epoch_ = 0;
+};
+
+enum { WIRE_F32 = 0, WIRE_BF16 = 1 };
+static inline size_t wire_bytes(int wire) { return wire == WIRE_BF16 ? 2 : 4; }
+
+// fp32 -> bf16 round-to-nearest-even (NaN stays NaN), the same rounding as cvt.rn.bf16.f32 on the device
+static inline uint16_t f32_to_bf16_bits(uint32_t u) {
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);
+  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+static void narrow_piece(uint16_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = f32_to_bf16_bits(src[i]);
+}
+static void widen_piece(uint32_t* __restrict__ dst, const uint16_t* __restrict__ src, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = static_cast<uint32_t>(src[i]) << 16;
+}
+static constexpr size_t kPieceElems = (size_t)1 << 19;   // 2 MiB of fp32 per work item
+// caller fp32 -> staging (plain copy or narrowing), spread over the host workers
+static void stage_in(void* dst, const float* src, size_t n, int wire) {
+  const int pieces = static_cast<int>((n + kPieceElems - 1) / kPieceElems);
+  HostWorkers::get().run(pieces, [&](int i) {
+    const size_t o = (size_t)i * kPieceElems, c = (n - o < kPieceElems) ? n - o : kPieceElems;
+    if (wire == WIRE_BF16)
+      narrow_piece(static_cast<uint16_t*>(dst) + o, reinterpret_cast<const uint32_t*>(src) + o, c);
+    else
+      memcpy(static_cast<float*>(dst) + o, src + o, c * 4);
+  });
+}
+// staging -> caller fp32 (plain copy or widening)
+static void stage_out(float* dst, const void* src, size_t n, int wire) {
+  const int pieces = static_cast<int>((n + kPieceElems - 1) / kPieceElems);
+  HostWorkers::get().run(pieces, [&](int i) {
+    const size_t o = (size_t)i * kPieceElems, c = (n - o < kPieceElems) ? n - o : kPieceElems;
+    if (wire == WIRE_BF16)
+      widen_piece(reinterpret_cast<uint32_t*>(dst) + o, static_cast<const uint16_t*>(src) + o, c);
+    else
+      memcpy(dst + o, static_cast<const float*>(src) + o, c * 4);
+  });
+}
+
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// ------------------------------------------------------------------------------------------------ per-device state
+static unsigned long long g_staging_fallbacks = 0;   // pinned ring could not be allocated -> direct (slow) copies
+
+struct PinnedRing {
+  static constexpr int S = 3;          // chunks in flight
+  char* base = nullptr;
+  size_t slot_bytes = 0;
+  cudaEvent_t ev[S] = {};
+  bool used[S] = {};
+  struct Pending {
+    float* dst;
+    const void* src;
+    size_t count;
+    int wire;
+  };
+  std::vector<Pending> pending[S];
+  bool ensure(size_t bytes) {
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    if (bytes <= slot_bytes) return true;
+    release();
+    if (cudaMallocHost(reinterpret_cast<void**>(&base), (size_t)S * bytes) != cudaSuccess) {
+      cudaGetLastError();
+      base = nullptr;
+      ++g_staging_fallbacks;
+      return false;
+    }
+    slot_bytes = bytes;
+    for (int i = 0; i < S; ++i)
+      if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        release();
+        return false;
+      }
+    return true;
+  }
+  void release() {
+    if (base) cudaFreeHost(base);
+    base = nullptr, slot_bytes = 0;
+    for (int i = 0; i < S; ++i) used[i] = false, pending[i].clear();
+  }
+  char* slot(int s) { return base + (size_t)s * slot_bytes; }
+  // a slot may be refilled once the copies that last read it have finished
+  cudaError_t acquire(int s) {
+    if (!used[s]) return cudaSuccess;
+    used[s] = false;
+    return cudaEventSynchronize(ev[s]);
+  }
+  cudaError_t mark(int s, cudaStream_t st) {
+    const cudaError_t e = cudaEventRecord(ev[s], st);
+    used[s] = (e == cudaSuccess);
+    return e;
+  }
+  // output side: wait for the slot's D2H copies, then hand the bytes to the caller's buffers
+  cudaError_t drain(int s) {
+    cudaError_t e = cudaSuccess;
+    if (used[s]) {
+      e = cudaEventSynchronize(ev[s]);
+      used[s] = false;
+    }
+    if (e == cudaSuccess)
+      for (const Pending& p : pending[s]) stage_out(p.dst, p.src, p.count, p.wire);
+    pending[s].clear();   // after an error nothing unverified is handed to the caller
+    return e;
+  }
+};
+
+struct DevPipe {
+  bool ready = false;
+  cudaStream_t in = nullptr, comp = nullptr, out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_comp;
+  PinnedRing rin, rout;
+  int init() {
+    if (ready) return FA_OK;
+    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+    FA_CUDA_CHECK(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+    ready = true;
+    return FA_OK;
+  }
+  int events(int n) {
+    while ((int)ev_in.size() < n) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      FA_CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      FA_CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      ev_in.push_back(a);
+      ev_comp.push_back(b);
+    }
+    return FA_OK;
+  }
+  cudaError_t drain() {
+    const cudaError_t e1 = cudaStreamSynchronize(in), e2 = cudaStreamSynchronize(comp), e3 = cudaStreamSynchronize(out);
+    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  }
+};
+static DevPipe g_pipes[ScratchPool::kMaxDev];
+static DevPipe* current_pipe() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= ScratchPool::kMaxDev) {
+    set_error(FA_ERR_CUDA, "legacy pipeline: bad current device");
+    return nullptr;
+  }
+  return g_pipes[d].init() == FA_OK ? &g_pipes[d] : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ chunk planning
+struct Chunk {
+  int b, nb, h0, hc;   // batches [b, b+nb) x heads [h0, h0+hc); nb > 1 only with all heads (one contiguous slab)
+};
+static size_t g_chunk_bytes = 0;   // 0 = unresolved: env MINITORCH_FA_CHUNK_MB, else 16 MiB (direct) / 64 MiB (staged)
+static bool g_chunk_explicit = false;
+// About chunk_bytes of fp32 per tensor and chunk: whole batches when a batch fits (small problems become ONE chunk:
+// every extra chunk costs ~10 driver calls), otherwise groups of heads inside one batch.  A chunk never straddles a
+// batch boundary unless it holds whole batches, so kv_len / the key mask index by the chunk's first batch.
+static void plan_chunks(int B, int nh, int N, int d, bool staged, std::vector<Chunk>& out) {
+  if (!g_chunk_bytes) {
+    const char* e = getenv("MINITORCH_FA_CHUNK_MB");
+    const long mb = e ? atol(e) : 16;
+    g_chunk_explicit = e != nullptr;
+    g_chunk_bytes = (size_t)(mb > 0 ? mb : 16) << 20;
+  }
+  const size_t chunk_bytes = (staged && !g_chunk_explicit) ? ((size_t)64 << 20) : g_chunk_bytes;
+  const size_t head_bytes = (size_t)N * d * 4;
+  const size_t batch_bytes = head_bytes * nh;
+  out.clear();
+  int hc = (int)(chunk_bytes / head_bytes);
+  hc = hc < 1 ? 1 : (hc > nh ? nh : hc);
+  if (hc == nh) {
+    size_t nb = batch_bytes <= chunk_bytes ? chunk_bytes / batch_bytes : 1;
+    if (nb < 1) nb = 1;
+    for (int b = 0; b < B; b += (int)nb) out.push_back(Chunk{b, (B - b < (int)nb) ? B - b : (int)nb, 0, nh});
+    return;
+  }
+  for (int b = 0; b < B; ++b)
+    for (int h0 = 0; h0 < nh; h0 += hc) out.push_back(Chunk{b, 1, h0, (nh - h0 < hc) ? nh - h0 : hc});
+}
+
+// ------------------------------------------------------------------------------------------------ masks
+// A LightSeq-style padding mask is "0 on the first kv_len[b] keys, a huge negative number after"
+// (kernel_tests/test_softmax_fw.py:44-45 uses -1e8).  When every row of the host mask has that shape (tail <= -1e6,
+// at least one valid key) the kernels skip whole KV tiles through kv_len[] instead of adding the mask per element.
+static bool mask_to_kv_len(const float* key_mask, int B, int N, int* kv_len_out) {
+  for (int b = 0; b < B; ++b) {
+    const float* r = key_mask + (size_t)b * N;
+    int n = 0;
+    while (n < N && r[n] == 0.0f) ++n;
+    if (n == 0) return false;
+    for (int j = n; j < N; ++j)
+      if (!(r[j] <= -1e6f)) return false;
+    kv_len_out[b] = n;
+  }
+  return true;
+}
+// Upload kv_len[] (fast path) or the additive mask; synchronous (tiny) so the host scratch can be reused.
+static int stage_mask(fa_attn_desc* a, const float* key_mask, int slot) {
+  if (!key_mask) return FA_OK;
+  const size_t bytes = (size_t)a->B * a->N * 4 + (size_t)a->B * 4 + 16;
+  char* d = static_cast<char*>(g_pool.get(slot, bytes));
+  if (!d) return set_error(FA_ERR_CUDA, "mask staging allocation failed");
+  std::vector<int> h_kv(a->B);
+  if (mask_to_kv_len(key_mask, a->B, a->N, h_kv.data())) {
+    FA_CUDA_CHECK(cudaMemcpy(d, h_kv.data(), (size_t)a->B * 4, cudaMemcpyHostToDevice));
+    a->kv_len = reinterpret_cast<const int*>(d);
+  } else {
+    char* dm = d + (((size_t)a->B * 4 + 15) & ~size_t(15));
+    FA_CUDA_CHECK(cudaMemcpy(dm, key_mask, (size_t)a->B * a->N * 4, cudaMemcpyHostToDevice));
+    a->key_mask = reinterpret_cast<const float*>(dm);
+  }
+  return FA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward cache
+// Device copies of one forward call's Q, K, V, O (wire dtype) and m, l (fp32), kept for the matching backward.
+static uint64_t fingerprint(const float* p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(p);
+  const size_t step = n / 61 + 1;
+  for (size_t i = 0; i < n; i += step) h = (h ^ u[i]) * 1099511628211ull;
+  if (n) h = (h ^ u[n - 1]) * 1099511628211ull;
+  return h ^ n;
+}
+struct FwdEntry {
+  int dev = -1, wire = 0, B = 0, nh = 0, N = 0, d = 0;
+  const float* host[6] = {};   // Q K V O m l
+  uint64_t fp[6] = {};
+  void* dptr[6] = {};
+  size_t bytes = 0;
+  unsigned long long stamp = 0;
+};
+static std::vector<FwdEntry> g_fwd_cache;
+static unsigned long long g_fwd_stamp = 0, g_fwd_hits = 0, g_fwd_misses = 0;
+static long long g_keep_budget = -1;   // bytes; resolved from MINITORCH_FA_KEEP_FWD_MB (default 4096, 0 disables)
+static size_t keep_budget() {
+  if (g_keep_budget < 0) {
+    const char* e = getenv("MINITORCH_FA_KEEP_FWD_MB");
+    g_keep_budget = (e ? atoll(e) : 4096ll) << 20;
+    if (g_keep_budget < 0) g_keep_budget = 0;
+  }
+  return (size_t)g_keep_budget;
+}
+static void free_entry(FwdEntry& e, cudaStream_t st) {
+  for (void*& p : e.dptr) {
+    if (p) cudaFreeAsync(p, st);
+    p = nullptr;
+  }
+}
+static void drop_cached_forwards(int dev, cudaStream_t st) {
+  for (size_t i = 0; i < g_fwd_cache.size();) {
+    if (g_fwd_cache[i].dev == dev) {
+      free_entry(g_fwd_cache[i], st);
+      g_fwd_cache.erase(g_fwd_cache.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+}
+// stream-ordered device allocation; on failure the cached forwards of this device are released and it is retried once
+static void* alloc_async(size_t bytes, cudaStream_t st, int dev) {
+  void* p = pool_alloc(bytes, st);
+  if (p) return p;
+  drop_cached_forwards(dev, st);
+  cudaStreamSynchronize(st);
+  return pool_alloc(bytes, st);
+}
+
+struct LegacyShape {
+  int B, nh, N, d;
+  size_t n() const { return (size_t)B * nh * N * d; }
+  size_t r() const { return (size_t)B * nh * N; }
+};
+
+static int fwd_tc_bf16(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, float* m, float* l,
+                       cudaStream_t st);   // defined in flashattention_kernel.cu
+
+// Common driver of the four legacy forward entry points.
+static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, float* m, const float* key_mask,
+                           int causal, int B, int nh, int N, int d) {
+  clear_error();
+  fa_attn_desc a{};
+  a.B = B, a.H = nh, a.N = N, a.d = d, a.causal = causal;
+  a.dtype = FA_DTYPE_F32;
+  if (validate(&a, "launch_flashattention_forward")) return;
+  if (!Q || !K || !V || !O || !l || !m) {
+    set_error(FA_ERR_INVALID, "launch_flashattention_forward: null host pointer");
+    return;
+  }
+  DevPipe* Pp = current_pipe();
+  if (!Pp) return;
+  DevPipe& P = *Pp;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const LegacyShape S{B, nh, N, d};
+  const size_t n = S.n(), r = S.r();
+  const bool tc = current_mode() == FA_MODE_BF16 && tc_head_dim(d);
+  const int wire = tc ? WIRE_BF16 : WIRE_F32;
+  const size_t esz = wire_bytes(wire);
+  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
+
+  // device tensors of this call (kept for the backward when the budget allows)
+  FwdEntry E;
+  E.dev = dev, E.wire = wire, E.B = B, E.nh = nh, E.N = N, E.d = d;
+  E.bytes = 4 * n * esz + 2 * r * 4;
+  const size_t sizes[6] = {n * esz, n * esz, n * esz, n * esz, r * 4, r * 4};
+  for (int i = 0; i < 6; ++i) {
+    E.dptr[i] = alloc_async(sizes[i], P.in, dev);
+    if (!E.dptr[i]) {
+      set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed (%zu bytes)", sizes[i]);
+      free_entry(E, P.in);
+      return;
+    }
+  }
+  char *dQ_ = static_cast<char*>(E.dptr[0]), *dK_ = static_cast<char*>(E.dptr[1]), *dV_ = static_cast<char*>(E.dptr[2]),
+       *dO_ = static_cast<char*>(E.dptr[3]);
+  float *dm = static_cast<float*>(E.dptr[4]), *dl = static_cast<float*>(E.dptr[5]);
+
+  // bf16 wire: always staged (the narrowing IS the staging copy); fp32 wire: only pageable buffers of some size
+  bool staged = tc || (n * 4 >= ((size_t)256 << 10) && (is_pageable(Q) || is_pageable(K) || is_pageable(V) || is_pageable(O)));
+  std::vector<Chunk> chunks;
+  plan_chunks(B, nh, N, d, staged, chunks);
+  const int nc = (int)chunks.size();
+  size_t max_cn = 0, max_cr = 0;
+  for (const Chunk& ck : chunks) {
+    const size_t cn = (size_t)ck.nb * ck.hc * N * d, cr = (size_t)ck.nb * ck.hc * N;
+    max_cn = cn > max_cn ? cn : max_cn, max_cr = cr > max_cr ? cr : max_cr;
+  }
+  const size_t in_tensor = (max_cn * esz + 255) & ~(size_t)255, stat_tensor = (max_cr * 4 + 255) & ~(size_t)255;
+  if (staged && !(P.rin.ensure(3 * in_tensor) && P.rout.ensure(in_tensor + 2 * stat_tensor))) {
+    if (tc) {
+      set_error(FA_ERR_CUDA, "launch_flashattention_forward: pinned staging allocation failed");
+      free_entry(E, P.in);
+      return;
+    }
+    staged = false;   // fp32 wire can still go straight from the caller's buffers (slow for pageable memory)
+  }
+  if (P.events(nc) != FA_OK) {
+    free_entry(E, P.in);
+    return;
+  }
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t x) {
+    if (e == cudaSuccess) e = x;
+  };
+  constexpr int RS = PinnedRing::S;
+  int rc = FA_OK, issued = 0, drained = 0;
+  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
+    const Chunk& ck = chunks[c];
+    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
+    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
+    const int s = c % RS;
+    if (staged) {
+      step(P.rin.acquire(s));
+      const float* src[3] = {Q + off, K + off, V + off};
+      char* dst[3] = {dQ_ + off * esz, dK_ + off * esz, dV_ + off * esz};
+      for (int t = 0; t < 3; ++t) {
+        char* st = P.rin.slot(s) + t * in_tensor;
+        stage_in(st, src[t], cn, wire);
+        step(cudaMemcpyAsync(dst[t], st, cn * esz, cudaMemcpyHostToDevice, P.in));
+      }
+      step(P.rin.mark(s, P.in));
+    } else {
+      step(cudaMemcpyAsync(dQ_ + off * 4, Q + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+      step(cudaMemcpyAsync(dK_ + off * 4, K + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+      step(cudaMemcpyAsync(dV_ + off * 4, V + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+    }
+    step(cudaEventRecord(P.ev_in[c], P.in));
+    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
+    fa_attn_desc ca = a;
+    ca.B = ck.nb, ca.H = ck.hc;
+    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
+    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
+    if (tc) {
+      ca.dtype = FA_DTYPE_BF16;
+      rc = fwd_tc_bf16(&ca, dQ_ + off * 2, dK_ + off * 2, dV_ + off * 2, dO_ + off * 2, dm + roff, dl + roff, P.comp);
+    } else {
+      rc = fa_flash_fwd_dev(&ca, dQ_ + off * 4, dK_ + off * 4, dV_ + off * 4, dO_ + off * 4, dm + roff, dl + roff,
+                            reinterpret_cast<fa_stream_t>(P.comp));
+    }
+    if (rc != FA_OK) break;
+    step(cudaEventRecord(P.ev_comp[c], P.comp));
+    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
+    if (staged) {
+      // slot s of the output ring was drained RS chunks ago (see the loop below), so it is free
+      char* so = P.rout.slot(s);
+      step(cudaMemcpyAsync(so, dO_ + off * esz, cn * esz, cudaMemcpyDeviceToHost, P.out));
+      step(cudaMemcpyAsync(so + in_tensor, dm + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
+      step(cudaMemcpyAsync(so + in_tensor + stat_tensor, dl + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
+      P.rout.pending[s].push_back({O + off, so, cn, wire});
+      P.rout.pending[s].push_back({m + roff, so + in_tensor, cr, WIRE_F32});
+      P.rout.pending[s].push_back({l + roff, so + in_tensor + stat_tensor, cr, WIRE_F32});
+      step(P.rout.mark(s, P.out));
+      ++issued;
+      while (issued - drained > RS - 1) step(P.rout.drain(drained++ % RS));
+    } else {
+      step(cudaMemcpyAsync(O + off, dO_ + off * 4, cn * 4, cudaMemcpyDeviceToHost, P.out));
+      step(cudaMemcpyAsync(m + roff, dm + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
+      step(cudaMemcpyAsync(l + roff, dl + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
+    }
+  }
+  if (staged) {
+    while (drained < issued) step(P.rout.drain(drained++ % RS));
+    for (int i = 0; i < RS; ++i) P.rout.pending[i].clear(), P.rout.used[i] = false;
+  }
+  // always drain: the caller owns the host buffers and may free them as soon as we return
+  const int saved = fa_last_status();
+  char saved_msg[512];
+  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
+  saved_msg[sizeof(saved_msg) - 1] = 0;
+  step(P.drain());
+  for (int i = 0; i < RS; ++i) P.rin.used[i] = false;
+  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
+  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_forward: %s", cudaGetErrorString(e));
+
+  // keep the device tensors for the backward, or let them go
+  const bool ok = fa_last_status() == FA_OK;
+  const size_t budget = keep_budget();
+  if (!ok || budget == 0 || E.bytes > budget) {
+    free_entry(E, P.comp);
+    return;
+  }
+  float* const hp[6] = {Q, K, V, O, m, l};
+  const size_t cnt[6] = {n, n, n, n, r, r};
+  for (int i = 0; i < 6; ++i) E.host[i] = hp[i], E.fp[i] = fingerprint(hp[i], cnt[i]);
+  E.stamp = ++g_fwd_stamp;
+  // a new forward over the same buffers replaces the old entry; then evict oldest-first down to the budget
+  for (size_t i = 0; i < g_fwd_cache.size();) {
+    FwdEntry& o = g_fwd_cache[i];
+    if (o.dev == dev && (o.host[0] == Q || o.host[3] == O)) {
+      free_entry(o, P.comp);
+      g_fwd_cache.erase(g_fwd_cache.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+  size_t total = E.bytes;
+  for (const FwdEntry& o : g_fwd_cache) total += o.bytes;
+  while ((total > budget || g_fwd_cache.size() >= 64) && !g_fwd_cache.empty()) {
+    size_t oldest = 0;
+    for (size_t i = 1; i < g_fwd_cache.size(); ++i)
+      if (g_fwd_cache[i].stamp < g_fwd_cache[oldest].stamp) oldest = i;
+    total -= g_fwd_cache[oldest].bytes;
+    int cur = dev;
+    if (g_fwd_cache[oldest].dev != cur) cudaSetDevice(g_fwd_cache[oldest].dev);
+    free_entry(g_fwd_cache[oldest], nullptr);
+    if (g_fwd_cache[oldest].dev != cur) cudaSetDevice(cur);
+    g_fwd_cache.erase(g_fwd_cache.begin() + oldest);
+  }
+  g_fwd_cache.push_back(E);
+}
+
+// Finds (and removes) the cached forward whose host tensors are exactly these.
+static bool take_cached_forward(int dev, int wire, const LegacyShape& S, float* const hp[6], FwdEntry* out) {
+  const size_t cnt[6] = {S.n(), S.n(), S.n(), S.n(), S.r(), S.r()};
+  for (size_t i = 0; i < g_fwd_cache.size(); ++i) {
+    FwdEntry& o = g_fwd_cache[i];
+    if (o.dev != dev || o.wire != wire || o.B != S.B || o.nh != S.nh || o.N != S.N || o.d != S.d) continue;
+    bool same = true;
+    for (int t = 0; t < 6 && same; ++t) same = o.host[t] == hp[t];
+    for (int t = 0; t < 6 && same; ++t) same = o.fp[t] == fingerprint(hp[t], cnt[t]);
+    if (!same) continue;
+    *out = o;
+    g_fwd_cache.erase(g_fwd_cache.begin() + i);
+    ++g_fwd_hits;
+    return true;
+  }
+  ++g_fwd_misses;
+  return false;
+}
+
+static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, float* dK, float* dV, float* dO,
+                            float* l, float* m, const float* key_mask, int causal, int B, int nh, int N, int d) {
+  clear_error();
+  fa_attn_desc a{};
+  a.B = B, a.H = nh, a.N = N, a.d = d, a.causal = causal;
+  a.dtype = FA_DTYPE_F32;
+  if (validate(&a, "launch_flashattention_backward")) return;
+  if (!Q || !K || !V || !O || !dQ || !dK || !dV || !dO || !l || !m) {
+    set_error(FA_ERR_INVALID, "launch_flashattention_backward: null host pointer");
+    return;
+  }
+  DevPipe* Pp = current_pipe();
+  if (!Pp) return;
+  DevPipe& P = *Pp;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const LegacyShape S{B, nh, N, d};
+  const size_t n = S.n(), r = S.r();
+  const bool tc = current_mode() == FA_MODE_BF16 && tc_head_dim(d);
+  const int wire = tc ? WIRE_BF16 : WIRE_F32;
+  const size_t esz = wire_bytes(wire);
+  if (stage_mask(&a, key_mask, 10) != FA_OK) return;
+
+  // inputs: Q K V O (wire dtype), m l (fp32) -- from the matching forward if it is still cached -- and dO
+  float* const hp[6] = {Q, K, V, O, m, l};
+  FwdEntry E;
+  const bool hit = take_cached_forward(dev, wire, S, hp, &E);
+  if (!hit) {
+    E = FwdEntry();
+    const size_t sizes[6] = {n * esz, n * esz, n * esz, n * esz, r * 4, r * 4};
+    for (int i = 0; i < 6; ++i) {
+      E.dptr[i] = alloc_async(sizes[i], P.in, dev);
+      if (!E.dptr[i]) {
+        set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed (%zu bytes)", sizes[i]);
+        free_entry(E, P.in);
+        return;
+      }
+    }
+  }
+  void* g[4] = {};   // dO, dQ, dK, dV on the device
+  for (int i = 0; i < 4; ++i) {
+    g[i] = alloc_async(n * esz, P.in, dev);
+    if (!g[i]) {
+      set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed (%zu bytes)", n * esz);
+      for (int k = 0; k < i; ++k) cudaFreeAsync(g[k], P.in);
+      free_entry(E, P.in);
+      return;
+    }
+  }
+  auto release_all = [&](cudaStream_t st) {
+    for (void* p : g) cudaFreeAsync(p, st);
+    free_entry(E, st);
+  };
+  char* din[5] = {static_cast<char*>(E.dptr[0]), static_cast<char*>(E.dptr[1]), static_cast<char*>(E.dptr[2]),
+                  static_cast<char*>(E.dptr[3]), static_cast<char*>(g[0])};
+  float *dm = static_cast<float*>(E.dptr[4]), *dl = static_cast<float*>(E.dptr[5]);
+  char* dout[3] = {static_cast<char*>(g[1]), static_cast<char*>(g[2]), static_cast<char*>(g[3])};
+  float* const host_in[5] = {Q, K, V, O, dO};
+  float* const host_out[3] = {dQ, dK, dV};
+  const int first_in = hit ? 4 : 0;   // a cached forward leaves only dO to upload
+
+  bool staged = tc;
+  if (!staged && n * 4 >= ((size_t)256 << 10)) {
+    bool any = is_pageable(dQ) || is_pageable(dK) || is_pageable(dV);
+    for (int i = first_in; i < 5; ++i) any = any || is_pageable(host_in[i]);
+    staged = any;
+  }
+  std::vector<Chunk> chunks;
+  plan_chunks(B, nh, N, d, staged, chunks);
+  const int nc = (int)chunks.size();
+  size_t max_cn = 0, max_cr = 0;
+  for (const Chunk& ck : chunks) {
+    const size_t cn = (size_t)ck.nb * ck.hc * N * d, cr = (size_t)ck.nb * ck.hc * N;
+    max_cn = cn > max_cn ? cn : max_cn, max_cr = cr > max_cr ? cr : max_cr;
+  }
+  const size_t in_tensor = (max_cn * esz + 255) & ~(size_t)255, stat_tensor = (max_cr * 4 + 255) & ~(size_t)255;
+  const size_t in_slot = (5 - first_in) * in_tensor + (hit ? 0 : 2 * stat_tensor);
+  if (staged && !(P.rin.ensure(in_slot) && P.rout.ensure(3 * in_tensor))) {
+    if (tc) {
+      set_error(FA_ERR_CUDA, "launch_flashattention_backward: pinned staging allocation failed");
+      release_all(P.in);
+      return;
+    }
+    staged = false;
+  }
+  if (P.events(nc) != FA_OK) {
+    release_all(P.in);
+    return;
+  }
+  cudaError_t e = cudaSuccess;
+  auto step = [&](cudaError_t x) {
+    if (e == cudaSuccess) e = x;
+  };
+  constexpr int RS = PinnedRing::S;
+  int rc = FA_OK, issued = 0, drained = 0;
+  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
+    const Chunk& ck = chunks[c];
+    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
+    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
+    const int s = c % RS;
+    if (staged) {
+      step(P.rin.acquire(s));
+      char* st = P.rin.slot(s);
+      for (int i = first_in; i < 5; ++i, st += in_tensor) {
+        stage_in(st, host_in[i] + off, cn, wire);
+        step(cudaMemcpyAsync(din[i] + off * esz, st, cn * esz, cudaMemcpyHostToDevice, P.in));
+      }
+      if (!hit) {
+        stage_in(st, m + roff, cr, WIRE_F32);
+        step(cudaMemcpyAsync(dm + roff, st, cr * 4, cudaMemcpyHostToDevice, P.in));
+        st += stat_tensor;
+        stage_in(st, l + roff, cr, WIRE_F32);
+        step(cudaMemcpyAsync(dl + roff, st, cr * 4, cudaMemcpyHostToDevice, P.in));
+      }
+      step(P.rin.mark(s, P.in));
+    } else {
+      for (int i = first_in; i < 5; ++i)
+        step(cudaMemcpyAsync(din[i] + off * 4, host_in[i] + off, cn * 4, cudaMemcpyHostToDevice, P.in));
+      if (!hit) {
+        step(cudaMemcpyAsync(dm + roff, m + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
+        step(cudaMemcpyAsync(dl + roff, l + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
+      }
+    }
+    step(cudaEventRecord(P.ev_in[c], P.in));
+    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
+    fa_attn_desc ca = a;
+    ca.B = ck.nb, ca.H = ck.hc;
+    ca.dtype = tc ? FA_DTYPE_BF16 : FA_DTYPE_F32;
+    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
+    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
+    const size_t o = off * esz;
+    rc = fa_flash_bwd_dev(&ca, din[0] + o, din[1] + o, din[2] + o, din[3] + o, din[4] + o, dm + roff, dl + roff,
+                          dout[0] + o, dout[1] + o, dout[2] + o, reinterpret_cast<fa_stream_t>(P.comp));
+    if (rc != FA_OK) break;
+    step(cudaEventRecord(P.ev_comp[c], P.comp));
+    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
+    if (staged) {
+      char* so = P.rout.slot(s);
+      for (int i = 0; i < 3; ++i) {
+        step(cudaMemcpyAsync(so + i * in_tensor, dout[i] + o, cn * esz, cudaMemcpyDeviceToHost, P.out));
+        P.rout.pending[s].push_back({host_out[i] + off, so + i * in_tensor, cn, wire});
+      }
+      step(P.rout.mark(s, P.out));
+      ++issued;
+      while (issued - drained > RS - 1) step(P.rout.drain(drained++ % RS));
+    } else {
+      for (int i = 0; i < 3; ++i)
+        step(cudaMemcpyAsync(host_out[i] + off, dout[i] + o, cn * 4, cudaMemcpyDeviceToHost, P.out));
+    }
+  }
+  if (staged) {
+    while (drained < issued) step(P.rout.drain(drained++ % RS));
+    for (int i = 0; i < RS; ++i) P.rout.pending[i].clear(), P.rout.used[i] = false;
+  }
+  const int saved = fa_last_status();
+  char saved_msg[512];
+  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
+  saved_msg[sizeof(saved_msg) - 1] = 0;
+  step(P.drain());
+  for (int i = 0; i < RS; ++i) P.rin.used[i] = false;
+  release_all(P.comp);
+  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
+  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
+}
+
+}  // namespace fa

@@ -38,6 +38,70 @@ def _make_like(ref, arr: np.ndarray):
     return out
 
 
+class _PinnedPool:
+    """fp32 numpy arrays over page-locked host memory (``fa_malloc_host``), recycled by size.
+
+    The outputs of the flash entry points (O, m, l, dQ, dK, dV) are allocated here when they are large: the library's
+    D2H copies / widening threads then write into memory that is already mapped and pinned instead of first-touching a
+    fresh ``numpy.zeros`` block page by page, and a later call that reads them (the backward reads O) skips staging.
+    A block returns to the free list when the last numpy view of it dies."""
+
+    MIN_BYTES = 1 << 20
+    MAX_CACHED = 8 << 30
+
+    def __init__(self):
+        self.free = {}
+        self.cached = 0
+
+    def _release(self, ptr, nbytes):
+        if self.cached + nbytes <= self.MAX_CACHED:
+            self.free.setdefault(nbytes, []).append(ptr)
+            self.cached += nbytes
+        else:
+            try:
+                _lib.load("flashattention_kernel").fa_free_host(ptr)
+            except Exception:
+                pass
+
+    def empty(self, count: int):
+        import ctypes
+        import weakref
+        nbytes = int(count) * 4
+        if nbytes < self.MIN_BYTES:
+            return None
+        lst = self.free.get(nbytes)
+        if lst:
+            ptr = lst.pop()
+            self.cached -= nbytes
+        else:
+            lib = _lib.load("flashattention_kernel")
+            ptr = lib.fa_malloc_host(nbytes)
+            if not ptr and self.free:       # pinned memory is exhausted: give the cached blocks back and retry
+                for nb, ptrs in self.free.items():
+                    for q in ptrs:
+                        lib.fa_free_host(q)
+                self.free, self.cached = {}, 0
+                ptr = lib.fa_malloc_host(nbytes)
+            if not ptr:
+                return None
+        buf = (ctypes.c_float * int(count)).from_address(ptr)
+        weakref.finalize(buf, self._release, ptr, nbytes)
+        return np.frombuffer(buf, dtype=datatype)
+
+
+_pinned = _PinnedPool()
+
+
+def _out_like(ref, shape):
+    """Output tensor of ref's class/backend; large ones live in pinned memory and are NOT zero-filled (the library
+    overwrites every element of its outputs)."""
+    count = int(np.prod(shape))
+    arr = _pinned.empty(count)
+    if arr is None:
+        return ref.zeros(tuple(shape))
+    return type(ref).make(arr, tuple(shape), backend=ref.backend)
+
+
 def _mask_ptr(key_mask, B, N):
     if key_mask is None:
         return None, None
@@ -191,9 +255,9 @@ class CudaKernelOps:
     def _flash_fw(Q, K, V, causal: bool, key_mask=None):
         lib = _lib.load("flashattention_kernel")
         B, nh, N, d = Q.shape
-        O = Q.zeros((B, nh, N, d))
-        l = Q.zeros((B, nh, N))
-        m = _make_like(Q, np.full((B, nh, N), -np.inf, dtype=datatype))
+        O, l, m = _out_like(Q, (B, nh, N, d)), _out_like(Q, (B, nh, N)), _out_like(Q, (B, nh, N))
+        if hasattr(m, "requires_grad_"):
+            m.requires_grad_(True)  # the reference creates m with requires_grad=True (:624-628)
         Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
         keep, kptr = _mask_ptr(key_mask, B, N)
         if key_mask is None and not causal:
@@ -212,7 +276,7 @@ class CudaKernelOps:
     def _flash_bw(Q, K, V, O, dO, m, l, causal: bool, key_mask=None):
         lib = _lib.load("flashattention_kernel")
         B, nh, N, d = Q.shape
-        dQ, dK, dV = Q.zeros((B, nh, N, d)), Q.zeros((B, nh, N, d)), Q.zeros((B, nh, N, d))
+        dQ, dK, dV = (_out_like(Q, (B, nh, N, d)) for _ in range(3))
         Q, K, V, O, dO, m, l = (t.contiguous() for t in (Q, K, V, O, dO, m, l))
         keep, kptr = _mask_ptr(key_mask, B, N)
         args = (_storage(Q), _storage(K), _storage(V), _storage(O), _storage(dQ), _storage(dK), _storage(dV),

@@ -44,6 +44,17 @@ class Aggregator:
     def max(self, x: float) -> float:
         return self._reduce(x, "MAX")
 
+    def gather(self, x: float) -> list:
+        """The value of every rank, in rank order (per-rank attribution of a max-over-ranks time)."""
+        if self.dist is None:
+            return [float(x)]
+        import torch
+        world = self.dist.get_world_size()
+        out = torch.zeros(world, dtype=torch.float64, device=self.device)
+        out[self.dist.get_rank()] = float(x)
+        self.dist.all_reduce(out, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in out.tolist()]
+
     def sum(self, x: float) -> float:
         return self._reduce(x, "SUM")
 

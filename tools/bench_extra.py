@@ -48,19 +48,20 @@ def time_call(fn, lib, reps=10, flush=True):
 
 
 def dev_rand(shape, seed, lo=-1.0, hi=1.0):
-    """uniform fp32 tensor on device, filled slice by slice to bound host memory"""
+    """uniform fp32 tensor on device: one 64 MiB random block tiled over the tensor (bandwidth does not depend on the
+    values, and gigabytes of host RNG would dominate the run)"""
     out = dev.DeviceArray(shape, "f32")
     lib = fb._lib.load("flashattention_kernel")
     n = out.size
-    rng = np.random.default_rng(seed)
     step = 1 << 24
+    h = np.random.default_rng(seed).uniform(lo, hi, min(step, n)).astype(np.float32)
     for s in range(0, n, step):
-        h = rng.uniform(lo, hi, min(step, n - s)).astype(np.float32)
-        lib.fa_h2d(c_void_p(out.ptr + 4 * s), h.ctypes.data_as(c_void_p), h.nbytes)
+        c = min(step, n - s)
+        lib.fa_h2d(c_void_p(out.ptr + 4 * s), h.ctypes.data_as(c_void_p), c * 4)
     return out
 
 
-def companions(P):
+def companions(P, quiet=False):
     sm = fb._lib.load("softmax_kernel")
     ln = fb._lib.load("layernorm_kernel")
     fl = fb._lib.load("flashattention_kernel")
@@ -102,7 +103,7 @@ def companions(P):
     return res
 
 
-def attn_case(P, B, H, N, d, causal, kv=None, bwd=False, reps=8):
+def attn_case(P, B, H, N, d, causal, kv=None, bwd=False, reps=8, quiet=False):
     fl = fb._lib.load("flashattention_kernel")
     rng = np.random.default_rng(0)
     base = dev.to_bf16_bits(rng.standard_normal((1, H, N, d)).astype(np.float32))
@@ -137,8 +138,9 @@ def attn_case(P, B, H, N, d, causal, kv=None, bwd=False, reps=8):
         r["bwd_frac_sustained"] = r["bwd_tflops"] / P["tf_sustained"]
         r["bwd_frac_burst"] = r["bwd_tflops"] / P["tf_burst"]
         r["bwd_frac_datasheet"] = r["bwd_tflops"] / 2250.0
-    print("case", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if "frac" not in k},
-          file=sys.stderr, flush=True)
+    if not quiet:
+        print("case", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if "frac" not in k},
+              file=sys.stderr, flush=True)
     return r
 
 
