@@ -135,6 +135,24 @@ int fa_flash_fwd_dev(const fa_attn_desc* desc, const void* Q, const void* K, con
 int fa_flash_bwd_dev(const fa_attn_desc* desc, const void* Q, const void* K, const void* V, const void* O,
                      const void* dO, const float* m, const float* l, void* dQ, void* dK, void* dV,
                      fa_stream_t stream);
+/* Decode shapes (additive; SURVEY.md 8(f)-3 -- the reference re-runs the whole prefix per generated token,
+ * project/run_machine_translation.py:299-325, and has no cache): ONE query token per (batch, head) against a key / value
+ * cache.  q, out: logical (B, H, d); k_cache, v_cache: logical (B, H, L_cap, d) of which the first L (or kv_len[b])
+ * positions are valid; element strides as below (0 => contiguous).  Split-KV over the cache so batch-1 decoding still
+ * fills the GPU; every visible cache byte is read once.  lse (optional, (B,H) fp32) receives log sum exp of the scaled
+ * scores.  dtype FA_DTYPE_F32 (head_dim % 4 == 0, <= 256) or FA_DTYPE_BF16 (head_dim % 8 == 0, <= 512). */
+typedef struct {
+  int B, H, d;
+  int L;          /* valid cache positions when kv_len is NULL */
+  int L_cap;      /* capacity of the cache along the position axis (0 => L) */
+  int dtype;      /* FA_DTYPE_* of q, caches and out */
+  long long q_stride_b, q_stride_h;
+  long long o_stride_b, o_stride_h;
+  long long cache_stride_b, cache_stride_h, cache_stride_n;
+  const int* kv_len;   /* device int32[B] or NULL */
+} fa_decode_desc;
+int fa_flash_decode_dev(const fa_decode_desc* desc, const void* q, const void* k_cache, const void* v_cache, void* out,
+                        float* lse, fa_stream_t stream);
 /* fp32 <-> bf16 element conversion on device (n elements). */
 int fa_cast_f32_to_bf16_dev(const float* src, void* dst_bf16, size_t n, fa_stream_t stream);
 int fa_cast_bf16_to_f32_dev(const void* src_bf16, float* dst, size_t n, fa_stream_t stream);

@@ -12,15 +12,15 @@ Layout:
 from . import _lib, device, sharding
 from ._lib import FlashAttnError
 from .cuda_kernel_ops import CudaKernelOps
-from .device_ops import DeviceKernelOps, DeviceStorage
+from .device_ops import DeviceKernelOps, DeviceStorage, KVCache
 from .tensor import (Attn_Softmax, EmbeddingLookup, SoftmaxCrossEntropy, FlashAttention, FlashAttentionCausal, HostTensor, LayerNorm, TensorBackend,
                      default_backend, logsumexp, one_hot, softmax, softmax_loss, GELU,
                      tensor_from_numpy)
 from . import modules_transformer
 from .modules_transformer import (DecoderLM, Dropout, Embedding, FeedForward, FusedLayerNorm, LayerNorm1d, Linear,
-                                  MultiHeadAttention, TransformerLayer, generate)
+                                  MultiHeadAttention, TransformerLayer, decode_step, generate, generate_cached)
 
 __all__ = ["CudaKernelOps", "DeviceKernelOps", "DeviceStorage", "TensorBackend", "HostTensor", "tensor_from_numpy", "default_backend", "FlashAttention",
            "FlashAttentionCausal", "Attn_Softmax", "LayerNorm", "FlashAttnError", "_lib", "device", "sharding", "softmax", "modules_transformer",
            "MultiHeadAttention", "Linear", "Dropout", "DecoderLM", "TransformerLayer", "FeedForward", "Embedding",
-           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU", "EmbeddingLookup", "SoftmaxCrossEntropy", "generate"]
+           "LayerNorm1d", "FusedLayerNorm", "softmax_loss", "logsumexp", "one_hot", "GELU", "EmbeddingLookup", "SoftmaxCrossEntropy", "generate", "generate_cached", "decode_step", "KVCache"]

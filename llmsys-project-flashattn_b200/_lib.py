@@ -35,6 +35,16 @@ class fa_attn_desc(ctypes.Structure):
     ]
 
 
+class fa_decode_desc(ctypes.Structure):
+    _fields_ = [
+        ("B", c_int), ("H", c_int), ("d", c_int), ("L", c_int), ("L_cap", c_int), ("dtype", c_int),
+        ("q_stride_b", c_longlong), ("q_stride_h", c_longlong),
+        ("o_stride_b", c_longlong), ("o_stride_h", c_longlong),
+        ("cache_stride_b", c_longlong), ("cache_stride_h", c_longlong), ("cache_stride_n", c_longlong),
+        ("kv_len", c_void_p),
+    ]
+
+
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, ndim=1, flags="C_CONTIGUOUS")
 
 # symbol -> (restype, argtypes); shared by all four libraries
@@ -81,6 +91,7 @@ SYMBOLS = {
         "launch_flashattention_backward_masked": (None, [_f32] * 10 + [c_void_p, c_int] + [c_int] * 4),
         "fa_flash_fwd_dev": (c_int, [POINTER(fa_attn_desc)] + [c_void_p] * 6 + [c_void_p]),
         "fa_flash_bwd_dev": (c_int, [POINTER(fa_attn_desc)] + [c_void_p] * 10 + [c_void_p]),
+        "fa_flash_decode_dev": (c_int, [POINTER(fa_decode_desc)] + [c_void_p] * 5 + [c_void_p]),
         "fa_cast_f32_to_bf16_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
         "fa_cast_bf16_to_f32_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
         "fa_attn_flops": (c_double, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int]),

@@ -16,6 +16,7 @@
 #include "flash_fp32.cuh"
 #include "flash_fwd_sm100.cuh"
 #include "flash_bwd_sm100.cuh"
+#include "flash_decode.cuh"
 
 namespace fa {
 
@@ -443,6 +444,89 @@ int fa_flash_bwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const 
     clear_error();
   }
   return bwd_simt<__nv_bfloat16>(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode shapes: one query token per (batch, head) against a KV cache (flash_decode.cuh).
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+template <typename T>
+static int launch_decode(const fa_decode_desc* a, const decode::Params& p, const void* q, const void* kc, const void* vc,
+                         void* out, cudaStream_t st) {
+  constexpr int VN = decode::Vec<T>::N;
+  const int nvec = a->d / VN;
+  dim3 grid(p.nsplit, a->H, a->B);
+  const size_t smem = sizeof(float) * decode::kWarps * a->d;
+#define FA_DEC_CASE(LPK, NV)                                                                                        \
+  decode::partial_kernel<T, LPK, NV><<<grid, decode::kWarps * 32, smem, st>>>(p, (const T*)q, (const T*)kc,        \
+                                                                               (const T*)vc, (T*)out)
+  if (nvec <= 1) FA_DEC_CASE(1, 1);
+  else if (nvec <= 2) FA_DEC_CASE(2, 1);
+  else if (nvec <= 4) FA_DEC_CASE(4, 1);
+  else if (nvec <= 8) FA_DEC_CASE(8, 1);
+  else if (nvec <= 16) FA_DEC_CASE(16, 1);
+  else if (nvec <= 32) FA_DEC_CASE(32, 1);
+  else FA_DEC_CASE(32, 2);
+#undef FA_DEC_CASE
+  fa::count_launch();
+  FA_CUDA_CHECK(cudaGetLastError());
+  if (p.nsplit > 1) {
+    decode::combine_kernel<T><<<dim3(a->H, a->B), 128, 0, st>>>(p, (T*)out);
+    fa::count_launch();
+    FA_CUDA_CHECK(cudaGetLastError());
+  }
+  return FA_OK;
+}
+extern "C" {
+
+int fa_flash_decode_dev(const fa_decode_desc* a, const void* q, const void* k_cache, const void* v_cache, void* out,
+                        float* lse, fa_stream_t stream) {
+  clear_error();
+  if (!a || !q || !k_cache || !v_cache || !out) return set_error(FA_ERR_INVALID, "fa_flash_decode_dev: null argument");
+  if (a->B <= 0 || a->H <= 0 || a->d <= 0 || a->L < 0 || a->B > 65535 || a->H > 65535)
+    return set_error(FA_ERR_INVALID, "fa_flash_decode_dev: bad shape B=%d H=%d d=%d L=%d", a->B, a->H, a->d, a->L);
+  if (a->dtype != FA_DTYPE_F32 && a->dtype != FA_DTYPE_BF16)
+    return set_error(FA_ERR_INVALID, "fa_flash_decode_dev: unknown dtype %d", a->dtype);
+  const int VN = a->dtype == FA_DTYPE_BF16 ? 8 : 4;
+  const int cap = a->L_cap > 0 ? a->L_cap : a->L;
+  decode::Params p{};
+  p.B = a->B, p.H = a->H, p.d = a->d, p.L = a->L, p.kv_len = a->kv_len;
+  p.q_sb = a->q_stride_b ? a->q_stride_b : (long long)a->H * a->d;
+  p.q_sh = a->q_stride_h ? a->q_stride_h : a->d;
+  p.o_sb = a->o_stride_b ? a->o_stride_b : (long long)a->H * a->d;
+  p.o_sh = a->o_stride_h ? a->o_stride_h : a->d;
+  const bool cdef = !a->cache_stride_b && !a->cache_stride_h && !a->cache_stride_n;
+  p.c_sb = cdef ? (long long)a->H * cap * a->d : a->cache_stride_b;
+  p.c_sh = cdef ? (long long)cap * a->d : a->cache_stride_h;
+  p.c_sn = cdef ? a->d : a->cache_stride_n;
+  if (a->d % VN || a->d / VN > 64 || p.q_sb % VN || p.q_sh % VN || p.c_sb % VN || p.c_sh % VN || p.c_sn % VN)
+    return set_error(FA_ERR_UNSUPPORTED,
+                     "fa_flash_decode_dev: head_dim %d / strides must be multiples of %d elements (16 bytes) and head_dim "
+                     "<= %d", a->d, VN, 64 * VN);
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->d);
+  p.lse = lse;
+  // split the cache so that about two waves of CTAs cover the 148 SMs, at least 256 keys per split
+  const int Lmax = a->kv_len ? cap : a->L;
+  int nsplit = (2 * 148 + a->B * a->H - 1) / (a->B * a->H);
+  const int max_split = (Lmax + 255) / 256;
+  nsplit = nsplit > max_split ? max_split : nsplit;
+  nsplit = nsplit < 1 ? 1 : (nsplit > 64 ? 64 : nsplit);
+  p.nsplit = nsplit;
+  p.chunk = (((Lmax + nsplit - 1) / nsplit) + 15) & ~15;
+  if (p.chunk < 16) p.chunk = 16;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* ws = nullptr;
+  if (nsplit > 1) {
+    const size_t units = (size_t)a->B * a->H * nsplit;
+    ws = static_cast<float*>(pool_alloc(sizeof(float) * units * (2 + a->d), st));
+    if (!ws) return set_error(FA_ERR_CUDA, "fa_flash_decode_dev: workspace allocation failed");
+    p.ws_ml = ws;
+    p.ws_o = ws + units * 2;
+  }
+  const int rc = (a->dtype == FA_DTYPE_BF16) ? launch_decode<__nv_bfloat16>(a, p, q, k_cache, v_cache, out, st)
+                                             : launch_decode<float>(a, p, q, k_cache, v_cache, out, st);
+  if (ws) cudaFreeAsync(ws, st);
+  return rc;
 }
 
 }  // extern "C" (device-pointer API above; the legacy host-pointer ABI follows)

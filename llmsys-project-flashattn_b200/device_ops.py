@@ -86,6 +86,16 @@ def _bf16_copy(t):
     return buf
 
 
+class KVCache:
+    """Keys and values of the positions decoded so far, resident in HBM: fp32 (B, nh, capacity, d) each."""
+
+    def __init__(self, B: int, nh: int, capacity: int, d: int):
+        self.B, self.nh, self.capacity, self.d = int(B), int(nh), int(capacity), int(d)
+        n = self.B * self.nh * self.capacity * self.d
+        self.k, self.v = DeviceStorage(n), DeviceStorage(n)
+        self.len = 0
+
+
 class DeviceKernelOps:
     cuda = True
     device_resident = True
@@ -292,6 +302,43 @@ class DeviceKernelOps:
     @staticmethod
     def flash_attention_causal_bw(Q, K, V, O, dO, m, l):
         return DeviceKernelOps._flash_bw(Q, K, V, O, dO, m, l, True)
+
+    # ---- decode shapes: KV cache + split-KV attention -------------------------------------------
+    @staticmethod
+    def kv_cache_new(B: int, nh: int, capacity: int, d: int) -> "KVCache":
+        return KVCache(B, nh, capacity, d)
+
+    @staticmethod
+    def kv_cache_append(cache: "KVCache", k, v) -> None:
+        """Copy the (B, nh, n_new, d) keys / values (any strides, e.g. the permuted views of
+        project_to_query_key_value) into positions [len, len + n_new) of the cache."""
+        lib = _lib.load("combine")
+        B, nh, n_new, d = k.shape
+        if (B, nh, d) != (cache.B, cache.nh, cache.d) or cache.len + n_new > cache.capacity:
+            raise ValueError(f"kv_cache_append: {k.shape} does not fit cache {cache.B, cache.nh, cache.capacity, cache.d} "
+                             f"at position {cache.len}")
+        osh = _i32((B, nh, n_new, d))
+        ost = _i32((nh * cache.capacity * d, cache.capacity * d, d, 1))
+        for t, buf in ((k, cache.k), (v, cache.v)):
+            ish, ist = _layout(t)
+            _lib.check(lib, lib.fa_map_dev(buf.ptr + cache.len * d * 4, osh, ost, 4, _st(t).ptr, ish, ist, 4,
+                                           _fn_id("id"), None))
+        cache.len += n_new
+
+    @staticmethod
+    def flash_decode(q, cache: "KVCache"):
+        """softmax(q K^T / sqrt(d)) V for ONE query token per (batch, head) against the cached positions:
+        q (B, nh, 1, d) -> (B, nh, 1, d), fp32.  Causality is implicit (the query is the newest position)."""
+        lib = _fa()
+        B, nh, one, d = q.shape
+        assert one == 1 and (B, nh, d) == (cache.B, cache.nh, cache.d)
+        q = q.contiguous()
+        out = q.zeros((B, nh, 1, d))
+        a = _lib.fa_decode_desc()
+        a.B, a.H, a.d, a.L, a.L_cap, a.dtype = B, nh, d, cache.len, cache.capacity, _lib.FA_DTYPE_F32
+        _lib.check(lib, lib.fa_flash_decode_dev(ctypes.byref(a), _st(q).ptr, cache.k.ptr, cache.v.ptr, _st(out).ptr,
+                                                None, None))
+        return out
 
     # ---- fused softmax / layernorm -----------------------------------------------------------------------------
     @staticmethod

@@ -158,6 +158,23 @@ class MultiHeadAttention(Module):
         return self.out_projection(attn.view(batch_size * seq_len, n_embd)).view(batch_size, seq_len, n_embd)
 
 
+    def forward_cached(self, x: HostTensor, cache) -> HostTensor:
+        """Decode-time forward (the reference has no cache): `x` holds only the NEW positions
+        (B, n_new, E); their keys / values are appended to `cache` and the queries attend to everything cached.
+        n_new == 1 runs the split-KV decode kernel; a longer block is the prefill of an EMPTY cache and goes
+        through the module's regular (causal) attention core."""
+        batch_size, n_new, n_embd = x.shape
+        ops = self.backend.ops
+        q, k, kT, v = self.project_to_query_key_value(x)
+        ops.kv_cache_append(cache, k, v)
+        if n_new == 1:
+            attn = ops.flash_decode(q, cache).view(batch_size, 1, n_embd)
+        else:
+            assert cache.len == n_new and self.causal, "prefill expects an empty cache and a causal module"
+            attn = self.self_attention(q, k if self.use_flash_attention else kT, v)
+        return self.out_projection(attn.view(batch_size * n_new, n_embd)).view(batch_size, n_new, n_embd)
+
+
 class Embedding(Module):
     """One-hot @ weights, exactly the reference's formulation (minitorch/modules_basic.py:29-71)."""
 
@@ -250,6 +267,13 @@ class TransformerLayer(Module):
         y = self.ln_2(a.contiguous().view(batch_size * seq_len, x_dim)).view(batch_size, seq_len, x_dim)
         return self.ff(y) + a
 
+    def forward_cached(self, x: HostTensor, cache) -> HostTensor:
+        batch_size, seq_len, x_dim = x.shape
+        a = self.ln_1(x.contiguous().view(batch_size * seq_len, x_dim)).view(batch_size, seq_len, x_dim)
+        a = self.attention.forward_cached(a, cache) + x
+        y = self.ln_2(a.contiguous().view(batch_size * seq_len, x_dim)).view(batch_size, seq_len, x_dim)
+        return self.ff(y) + a
+
 
 class DecoderLM(Module):
     """Decoder-only Pre-LN transformer with four layers (minitorch/modules_transfomer.py:339-453); config #2 of
@@ -284,6 +308,47 @@ class DecoderLM(Module):
             x = layer(x)
         x = self.ln(x.contiguous().view(batch_size * seq_len, self.n_embd))
         return self.lm_head(x).view(batch_size, seq_len, self.n_vocab)
+
+
+def _layers(model):
+    return (model.t_layer_1, model.t_layer_2, model.t_layer_3, model.t_layer_4)
+
+
+def decode_step(model: DecoderLM, new_ids, caches) -> HostTensor:
+    """Logits (B, n_new, n_vocab) of the NEW positions only; `caches` (one KVCache per layer) hold the rest."""
+    ids = np.asarray(new_ids, dtype=datatype)
+    batch_size, n_new = ids.shape
+    start = caches[0].len
+    idx = tensor_from_numpy(ids, backend=model.backend)
+    pos = tensor_from_numpy(np.arange(start, start + n_new, dtype=datatype).reshape(1, n_new), backend=model.backend)
+    x = model.token_embeddings(idx) + model.position_embeddings(pos).view(1, n_new, model.n_embd)
+    for layer, cache in zip(_layers(model), caches):
+        x = layer.forward_cached(x, cache)
+    x = model.ln(x.contiguous().view(batch_size * n_new, model.n_embd))
+    return model.lm_head(x).view(batch_size, n_new, model.n_vocab)
+
+
+def generate_cached(model: DecoderLM, token_ids, model_max_length: int, eos_id: int = -1):
+    """Greedy decoding with a KV cache: the prompt is run once (prefill), then every new token costs ONE position
+    through the layers and one split-KV decode-attention call per layer, instead of the reference's full-prefix
+    re-run per token (project/run_machine_translation.py:299-325).  Same tokens as generate() (tests pin that).
+    Needs a device-resident backend (DeviceKernelOps: kv_cache_new / kv_cache_append / flash_decode)."""
+    ops = model.backend.ops
+    if not hasattr(ops, "flash_decode"):
+        raise RuntimeError("generate_cached needs a backend with a KV cache (TensorBackend(DeviceKernelOps))")
+    model.eval()
+    ids = [int(t) for t in token_ids]
+    attn = model.t_layer_1.attention
+    caches = [ops.kv_cache_new(1, attn.n_head, model_max_length + 1, attn.attn_hidden_dim) for _ in _layers(model)]
+    new = list(ids)
+    while len(ids) <= model_max_length:
+        logits = decode_step(model, np.asarray(new, dtype=datatype).reshape(1, len(new)), caches)
+        gen_id = int(np.argmax(logits.to_numpy()[0, len(new) - 1, :]))
+        if gen_id == eos_id:
+            break
+        ids.append(gen_id)
+        new = [gen_id]
+    return ids
 
 
 def generate(model: DecoderLM, token_ids, model_max_length: int, eos_id: int = -1):
