@@ -129,16 +129,30 @@ __global__ void reduce_kernel(float* __restrict__ out, Layout lo, const float* _
 struct MMStrides {
   long long ab, am, ak, bb, bk, bn, ob, om, on;
 };
+// Long contractions (K in the 10^5 range: the weight-gradient matmuls x^T @ dy over batch*seq rows) are (a) accumulated
+// in two levels -- an inner fp32 accumulator flushed into an outer one every kFlushK steps, so the rounding error grows
+// like sqrt(kFlushK) + sqrt(K / kFlushK) instead of sqrt(K) ulps (the reference's tests compare against torch at 1e-5) --
+// and (b) split over `splits` CTAs per output tile when the output alone cannot fill the GPU; the partial sums go to
+// a workspace [split][batch][M][N] and splitk_reduce_kernel adds them up in fp64.
+// The host-pointer MatrixMultiply (PCIe-bound anyway) accumulates in fp64 (AccT = double: every fp32 product is exact in
+// fp64, so a dot product carries one final rounding; B200 issues DFMA at half the FFMA rate): the reference's tests hold
+// 67-million-element gradients to atol = rtol = 1e-5 against torch's CPU GEMM, which leaves no room for our own sqrt(K)
+// ulps on top of torch's.  The device-resident fa_matmul_dev keeps fp32 accumulators (AccT = float, two levels).
+constexpr int kFlushK = 512;
+template <typename AccT>
 __global__ void __launch_bounds__(256) matmul_kernel(float* __restrict__ out, const float* __restrict__ A,
-                                                     const float* __restrict__ Bm, MMStrides st, int M, int N, int K) {
+                                                     const float* __restrict__ Bm, MMStrides st, int M, int N, int K,
+                                                     int splits, int k_chunk, float* __restrict__ ws) {
   __shared__ __align__(16) float As[16][64 + 4];   // [k][m]
   __shared__ __align__(16) float Bs[16][64 + 4];   // [k][n]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, b = blockIdx.z;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, b = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int k_lo = sp * k_chunk;
+  K = min(K, k_lo + k_chunk);
   const float* Ab = A + b * st.ab;
   const float* Bb = Bm + b * st.bb;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  AccT acc[4][4] = {}, tot[4][4] = {};
+  for (int k0 = k_lo; k0 < K; k0 += 16) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int idx = threadIdx.x + t * 256;   // 1024 elements per tile
@@ -158,13 +172,19 @@ __global__ void __launch_bounds__(256) matmul_kernel(float* __restrict__ out, co
     for (int kk = 0; kk < 16; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      const AccT av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+    if (sizeof(AccT) == 4 && ((k0 - k_lo) & (kFlushK - 1)) == kFlushK - 16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tot[i][j] += acc[i][j], acc[i][j] = 0.f;
+    }
   }
   float* Ob = out + b * st.ob;
 #pragma unroll
@@ -172,8 +192,25 @@ __global__ void __launch_bounds__(256) matmul_kernel(float* __restrict__ out, co
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
-      if (gm < M && gn < N) Ob[gm * st.om + gn * st.on] = acc[i][j];
+      if (gm < M && gn < N) {
+        const float v = static_cast<float>(tot[i][j] + acc[i][j]);
+        if (splits > 1) ws[((static_cast<long long>(sp) * (gridDim.z / splits) + b) * M + gm) * N + gn] = v;
+        else Ob[gm * st.om + gn * st.on] = v;
+      }
     }
+}
+
+// out[b, i, j] = sum over splits of ws[split][b][i][j], added in fp64
+__global__ void splitk_reduce_kernel(float* __restrict__ out, const float* __restrict__ ws, MMStrides st, int batch, int M,
+                                     int N, int splits) {
+  const long long total = static_cast<long long>(batch) * M * N;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += static_cast<double>(__ldg(ws + s * total + i));
+    const int gn = static_cast<int>(i % N), gm = static_cast<int>((i / N) % M), b = static_cast<int>(i / (static_cast<long long>(M) * N));
+    out[b * st.ob + gm * st.om + gn * st.on] = static_cast<float>(acc);
+  }
 }
 
 
@@ -281,12 +318,16 @@ __global__ void softmax_xent_bw_kernel(float* __restrict__ dx, const float* __re
 // Large-problem variant: 128x128 output tile, 8x8 register micro-tile per thread (256 threads), K step 16, the next
 // K slab prefetched into registers while the current one is multiplied out of shared memory.  Same arbitrary-stride
 // operand addressing as matmul_kernel; used when both M and N reach 128 (Linear / embedding / lm_head matmuls).
+template <typename AccT>
 __global__ void __launch_bounds__(256) matmul128_kernel(float* __restrict__ out, const float* __restrict__ A,
-                                                        const float* __restrict__ Bm, MMStrides st, int M, int N, int K) {
+                                                        const float* __restrict__ Bm, MMStrides st, int M, int N, int K,
+                                                        int splits, int k_chunk, float* __restrict__ ws) {
   __shared__ __align__(16) float As[16][128 + 4];   // [k][m]
   __shared__ __align__(16) float Bs[16][128 + 4];   // [k][n]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128, b = blockIdx.z;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128, b = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int k_lo = sp * k_chunk;
+  K = min(K, k_lo + k_chunk);
   const float* Ab = A + b * st.ab;
   const float* Bb = Bm + b * st.bb;
   // loader mapping: A slab 128(m) x 16(k): thread -> k = tid & 15, m = (tid >> 4) + 16 * t  (t = 0..7)
@@ -303,9 +344,10 @@ __global__ void __launch_bounds__(256) matmul128_kernel(float* __restrict__ out,
       rb[t] = (gn < N && gk2 < K) ? __ldg(Bb + gk2 * st.bk + gn * st.bn) : 0.f;
     }
   };
-  float acc[8][8] = {};
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  AccT acc[8][8] = {};
+  float tot[sizeof(AccT) == 4 ? 8 : 1][8] = {};
+  fetch(k_lo);
+  for (int k0 = k_lo; k0 < K; k0 += 16) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       As[a_k][a_m + 16 * t] = ra[t];
@@ -319,14 +361,22 @@ __global__ void __launch_bounds__(256) matmul128_kernel(float* __restrict__ out,
       const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
       const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const AccT av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const AccT bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+    if constexpr (sizeof(AccT) == 4) {
+      if (((k0 - k_lo) & (kFlushK - 1)) == kFlushK - 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tot[i][j] += acc[i][j], acc[i][j] = 0;
+      }
+    }
   }
   float* Ob = out + b * st.ob;
 #pragma unroll
@@ -336,20 +386,50 @@ __global__ void __launch_bounds__(256) matmul128_kernel(float* __restrict__ out,
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-      if (gn < N) Ob[gm * st.om + gn * st.on] = acc[i][j];
+      if (gn < N) {
+        float v;
+        if constexpr (sizeof(AccT) == 4) v = tot[i][j] + acc[i][j];
+        else v = static_cast<float>(acc[i][j]);
+        if (splits > 1) ws[((static_cast<long long>(sp) * (gridDim.z / splits) + b) * M + gm) * N + gn] = v;
+        else Ob[gm * st.om + gn * st.on] = v;
+      }
     }
   }
 }
 
-static void launch_matmul(float* out, const float* a, const float* b, const MMStrides& st, int batch, int m, int p, int n,
-                          cudaStream_t stream) {
-  if (m >= 128 && p >= 128) {
-    dim3 grid((p + 127) / 128, (m + 127) / 128, batch);
-    matmul128_kernel<<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n);
-  } else {
-    dim3 grid((p + 63) / 64, (m + 63) / 64, batch);
-    matmul_kernel<<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n);
+static int launch_matmul(float* out, const float* a, const float* b, const MMStrides& st, int batch, int m, int p, int n,
+                         cudaStream_t stream, bool f64acc = false) {
+  const bool big = m >= 128 && p >= 128;
+  const int tile = big ? 128 : 64;
+  const long long tiles = static_cast<long long>((p + tile - 1) / tile) * ((m + tile - 1) / tile) * batch;
+  // split the contraction when the output tiles alone leave most of the 148 SMs idle (weight-gradient shapes)
+  int splits = 1, k_chunk = n;
+  if (n >= 4096 && tiles < 2 * 148) {
+    splits = static_cast<int>((2 * 148 + tiles - 1) / tiles);
+    const int max_splits = (n + 1023) / 1024;
+    splits = splits > max_splits ? max_splits : splits;
+    splits = splits > 256 ? 256 : splits;
+    k_chunk = (((n + splits - 1) / splits) + 15) & ~15;
+    splits = (n + k_chunk - 1) / k_chunk;
   }
+  float* ws = nullptr;
+  if (splits > 1) {
+    ws = static_cast<float*>(pool_alloc(sizeof(float) * splits * batch * static_cast<size_t>(m) * p, stream));
+    if (!ws) return set_error(FA_ERR_CUDA, "matmul: split-K workspace allocation failed");
+  }
+  dim3 grid((p + tile - 1) / tile, (m + tile - 1) / tile, batch * splits);
+  if (big && f64acc) matmul128_kernel<double><<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n, splits, k_chunk, ws);
+  else if (big) matmul128_kernel<float><<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n, splits, k_chunk, ws);
+  else if (f64acc) matmul_kernel<double><<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n, splits, k_chunk, ws);
+  else matmul_kernel<float><<<grid, 256, 0, stream>>>(out, a, b, st, m, p, n, splits, k_chunk, ws);
+  if (splits > 1) {
+    const long long total = static_cast<long long>(batch) * m * p;
+    splitk_reduce_kernel<<<static_cast<int>((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256), 256, 0, stream>>>(
+        out, ws, st, batch, m, p, splits);
+    count_launch();
+    cudaFreeAsync(ws, stream);
+  }
+  return FA_OK;
 }
 
 static bool make_layout(Layout* l, const int* shape, const int* strides, int nd) {
@@ -514,7 +594,7 @@ void MatrixMultiply(float* out, int* out_shape, int* out_strides, float* a_stora
   st.bb = (b_shape[0] > 1) ? b_strides[0] : 0;
   st.bk = b_strides[1], st.bn = b_strides[2];
   st.ob = out_strides[0], st.om = out_strides[1], st.on = out_strides[2];
-  launch_matmul(d_out, d_a, d_b, st, batch, m, p, n, 0);
+  launch_matmul(d_out, d_a, d_b, st, batch, m, p, n, 0, /*f64acc=*/true);
   count_launch();
   CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * eo, cudaMemcpyDeviceToHost, 0));

@@ -43,6 +43,7 @@ namespace sm100 {
 struct BwdParams {
   int B, H, N, Npad;
   const int* kv_len;
+  const float* key_mask;   // (B, N) additive mask or nullptr (template MASK2)
   const float* lse2;   // (B*H, Npad) NEGATED log2-domain LSE (an FFMA2 addend); -inf for rows >= N
   const float* dvec;   // (B*H, Npad) D_i; 0 for rows >= N
   float* dq_acc;       // (B,H,N,D) fp32, zero-initialised
@@ -61,6 +62,10 @@ struct BwdParams {
 #else
 #define FA_TR(slot)
 #define FA_TRW(slot)
+#endif
+
+#ifndef FA_BWD_DQ_RED
+#define FA_BWD_DQ_RED 0   // 0: dQ through shared-memory staging + TMA add-reduce; 1 / 2: red.global.v4 from registers
 #endif
 
 template <int D>
@@ -167,7 +172,7 @@ __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
   return r;
 }
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, bool MASK2>
 __global__ void __launch_bounds__(640, 1)
     bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(640, 1)
       // Warp 18 + hh serves the warpgroups (., hh): staging box hh receives columns [D/2*hh + 32*c2, +32) of
       // dQ_it from warpgroup (it & 1, hh); one lane turns each fill into a TMA add-reduction and hands the
       // box to its next user once the TMA has read it.  The two halves never wait for each other.
-#ifndef FA_EXP_NODRAIN
+#if !defined(FA_EXP_NODRAIN) && !FA_BWD_DQ_RED
       if (lane == 0) {
         constexpr int PER_WG = D / 64;   // 32-column boxes per warpgroup and iteration
         const int hh = warp - 18;
@@ -436,6 +441,12 @@ __global__ void __launch_bounds__(640, 1)
     uint8_t* stg_row = sStg + j * 128;
     const int jx = j & 7;
     const uint64_t sc2 = f32x2(p.scale_log2, p.scale_log2);
+    // generic additive key mask: in the transposed layout a thread owns ONE key, so the mask is a per-thread scalar.
+    // It is added to the scaled score BEFORE the (negated) LSE, the order the forward uses (a -1e8 "padding" mask
+    // swallows the score in fp32 there, too -- the two passes have to round alike).
+    float mk = 0.f;
+    if (MASK2 && (k0 + j) < p.N) mk = __ldg(p.key_mask + static_cast<long long>(b) * p.N + k0 + j) * 1.4426950408889634f;
+    const uint64_t mk2 = f32x2(mk, mk);
 #ifdef FA_TRACE
     long long* trw = (hh == 0) ? tr : nullptr;   // lane 0 of every warp of the hh = 0 warpgroups
     if (w != 0 || hh != 0) tr = nullptr;
@@ -470,8 +481,13 @@ __global__ void __launch_bounds__(640, 1)
           const float4 l4 = *reinterpret_cast<const float4*>(nlse + 4 * c4);
 #endif
           float x0, x1, x2, x3;
-          f32x2_unpack(fma_f32x2(f32x2(s[4 * c4], s[4 * c4 + 1]), sc2, f32x2(l4.x, l4.y)), x0, x1);
-          f32x2_unpack(fma_f32x2(f32x2(s[4 * c4 + 2], s[4 * c4 + 3]), sc2, f32x2(l4.z, l4.w)), x2, x3);
+          if (MASK2) {
+            f32x2_unpack(add_f32x2(fma_f32x2(f32x2(s[4 * c4], s[4 * c4 + 1]), sc2, mk2), f32x2(l4.x, l4.y)), x0, x1);
+            f32x2_unpack(add_f32x2(fma_f32x2(f32x2(s[4 * c4 + 2], s[4 * c4 + 3]), sc2, mk2), f32x2(l4.z, l4.w)), x2, x3);
+          } else {
+            f32x2_unpack(fma_f32x2(f32x2(s[4 * c4], s[4 * c4 + 1]), sc2, f32x2(l4.x, l4.y)), x0, x1);
+            f32x2_unpack(fma_f32x2(f32x2(s[4 * c4 + 2], s[4 * c4 + 3]), sc2, f32x2(l4.z, l4.w)), x2, x3);
+          }
           float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
           if (masked) {
             if (!key_ok || 4 * c4 + 0 < cmin) e0 = 0.f;
@@ -541,7 +557,62 @@ __global__ void __launch_bounds__(640, 1)
       tc_fence_before();
       mbar_arrive(&dq_free[g]);          // T_dP may be overwritten by dP(it+1)
       FA_TR(14)
-#ifndef FA_EXP_NODRAIN   // (timing-only experiment: dQ is read out of TMEM and dropped)
+#if FA_BWD_DQ_RED
+      // dQ_i straight from registers into the fp32 accumulator with vector reductions (no shared-memory staging, no
+      // TMA): a thread owns 64 consecutive floats of its query row.  With FA_BWD_DQ_RED == 2 lane pairs swap half of
+      // their float4s first so that the two lanes of a pair complete one 32-byte sector per instruction.
+      {
+        const long long rowi = (static_cast<long long>(b) * p.H + h) * p.N + q0 + j;
+        float* dst = p.dq_acc + rowi * D + (D / 2) * hh;
+        const bool row_ok = (q0 + j) < p.N;
+#if FA_BWD_DQ_RED == 2
+        const bool odd = (lane & 1) != 0;
+        const long long prow = odd ? -static_cast<long long>(D) : static_cast<long long>(D);   // partner's row
+        const bool prow_ok = (q0 + (j ^ 1)) < p.N;
+#pragma unroll
+        for (int c2 = 0; c2 < D / 64; ++c2) {
+#pragma unroll
+          for (int s8 = 0; s8 < 4; ++s8) {   // a 32-byte sector = float4 pair (2*s8, 2*s8+1) of this 32-column piece
+            uint32_t mine[4], give[4], got[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              // even lane keeps its LOW float4 and gives its HIGH one; odd lane keeps HIGH and gives LOW
+              mine[x] = odd ? dq[c2][8 * s8 + 4 + x] : dq[c2][8 * s8 + x];
+              give[x] = odd ? dq[c2][8 * s8 + x] : dq[c2][8 * s8 + 4 + x];
+              got[x] = __shfl_xor_sync(0xffffffffu, give[x], 1);
+            }
+            // instruction 1: both lanes write the EVEN lane's row (even: own low half, odd: even's high half);
+            // instruction 2: both lanes write the ODD lane's row (even: odd's low half, odd: own high half)
+            float* a1 = dst + 32 * c2 + 8 * s8 + (odd ? (4 - D) : 0);      // even lane's row
+            float* a2 = dst + 32 * c2 + 8 * s8 + (odd ? 4 : D);            // odd lane's row
+            const bool ok1 = odd ? prow_ok : row_ok, ok2 = odd ? row_ok : prow_ok;
+            const uint32_t* v1 = odd ? got : mine;
+            const uint32_t* v2 = odd ? mine : got;
+            (void)prow;
+            if (ok1)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a1), "f"(__uint_as_float(v1[0])),
+                           "f"(__uint_as_float(v1[1])), "f"(__uint_as_float(v1[2])), "f"(__uint_as_float(v1[3]))
+                           : "memory");
+            if (ok2)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a2), "f"(__uint_as_float(v2[0])),
+                           "f"(__uint_as_float(v2[1])), "f"(__uint_as_float(v2[2])), "f"(__uint_as_float(v2[3]))
+                           : "memory");
+          }
+        }
+#else
+        if (row_ok) {
+#pragma unroll
+          for (int c2 = 0; c2 < D / 64; ++c2)
+#pragma unroll
+            for (int u8 = 0; u8 < 8; ++u8)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 * c2 + 4 * u8),
+                           "f"(__uint_as_float(dq[c2][4 * u8])), "f"(__uint_as_float(dq[c2][4 * u8 + 1])),
+                           "f"(__uint_as_float(dq[c2][4 * u8 + 2])), "f"(__uint_as_float(dq[c2][4 * u8 + 3]))
+                           : "memory");
+        }
+#endif
+      }
+#elif !defined(FA_EXP_NODRAIN)   // (FA_EXP_NODRAIN: timing-only experiment, dQ is read out of TMEM and dropped)
 #pragma unroll
       for (int c2 = 0; c2 < D / 64; ++c2) {
         // use number u of staging box hh by THIS warpgroup; group 0's very first use finds the box free

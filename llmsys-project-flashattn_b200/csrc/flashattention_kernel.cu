@@ -241,12 +241,12 @@ static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   return set_error(FA_ERR_UNSUPPORTED, "flash fwd (tensor core): head_dim %d not supported", a->d);
 }
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, bool MASK2>
 static int launch_bwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const CUtensorMap& tdo, const CUtensorMap& tdq, const sm100::BwdParams& bp,
                          cudaStream_t st) {
   using Cfg = sm100::BwdCfg<D>;
-  auto kern = sm100::bwd_kernel<D, CAUSAL>;
+  auto kern = sm100::bwd_kernel<D, CAUSAL, MASK2>;
   FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((a->N + 127) / 128, a->H, a->B);
   kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, tdq, bp);
@@ -255,11 +255,9 @@ static int launch_bwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUt
   return FA_OK;
 }
 
-// Tensor-core backward (bf16, head_dim 64/128, kv_len or no mask).  Returns FA_ERR_UNSUPPORTED for
-// configurations it does not cover (generic additive key mask) so the caller can use the CUDA-core path.
+// Tensor-core backward (bf16, head_dim 64/128; no mask, kv_len and / or a generic additive key mask).
 static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                   const float* m, const float* l, void* dQ, void* dK, void* dV, cudaStream_t st) {
-  if (a->key_mask) return FA_ERR_UNSUPPORTED;
   Strides s = resolve_strides(a);
   const int Npad = ((a->N + 127) / 128) * 128;
   const size_t rows_pad = (size_t)a->B * a->H * Npad;
@@ -307,16 +305,20 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   sm100::BwdParams bp;
   bp.B = a->B, bp.H = a->H, bp.N = a->N, bp.Npad = Npad;
   bp.kv_len = a->kv_len;
+  bp.key_mask = a->key_mask;
   bp.lse2 = lse2, bp.dvec = dvec, bp.dq_acc = acc;
   bp.dK = dK, bp.dV = dV;
   bp.sb = s.sb, bp.sh = s.sh, bp.sn = s.sn;
   bp.scale = 1.0f / sqrtf((float)a->d);
   bp.scale_log2 = bp.scale * 1.4426950408889634f;
   bp.trace = g_trace;
-  if (a->d == 128) rc = a->causal ? launch_bwd_tc<128, true>(a, tq, tk, tv, tdo, tdq, bp, st)
-                                  : launch_bwd_tc<128, false>(a, tq, tk, tv, tdo, tdq, bp, st);
-  else rc = a->causal ? launch_bwd_tc<64, true>(a, tq, tk, tv, tdo, tdq, bp, st)
-                      : launch_bwd_tc<64, false>(a, tq, tk, tv, tdo, tdq, bp, st);
+  rc = FA_ERR_UNSUPPORTED;
+#define FA_BWD_CASE(DD, CC, MM)                                                       \
+  if (a->d == DD && (a->causal != 0) == CC && (a->key_mask != nullptr) == MM)         \
+    rc = launch_bwd_tc<DD, CC, MM>(a, tq, tk, tv, tdo, tdq, bp, st);
+  FA_BWD_CASE(128, false, false) FA_BWD_CASE(128, true, false) FA_BWD_CASE(128, false, true) FA_BWD_CASE(128, true, true)
+  FA_BWD_CASE(64, false, false) FA_BWD_CASE(64, true, false) FA_BWD_CASE(64, false, true) FA_BWD_CASE(64, true, true)
+#undef FA_BWD_CASE
   if (rc) return rc;
   {
     const long long total8 = (long long)nacc / 8;
