@@ -113,6 +113,23 @@ __device__ __forceinline__ void gemm_tn(float (&acc)[4][4], const float* P, cons
   }
 }
 
+// Two-level accumulation for the gradient sums: a tile's 64-term partial sums are formed in a fresh accumulator and
+// then added to the running total, so the rounding error of a sum over N keys (queries) grows like sqrt(64) + sqrt(N/64)
+// ulps instead of sqrt(N).  (Measured against torch's fp32 CPU GEMMs through the reference's own test at N = 2048:
+// the single-chain sums were the largest term of the X.grad error budget.)
+__device__ __forceinline__ void add_into(float (&acc)[4][4], const float (&part)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
+}
+__device__ __forceinline__ void zero16(float (&part)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
+}
+
 // max / sum over the 16 lanes (tx) that share a score row
 __device__ __forceinline__ float row16_max(float v) {
 #pragma unroll
@@ -345,13 +362,18 @@ __global__ void __launch_bounds__(NT) bwd_dkdv_kernel(AttnParams p, const T* __r
       for (int c = 0; c < NCH; ++c) {
         const int c0 = col_base + c * 64;
         if (c0 < p.d) {
+          float part[4][4];
           load_tile<64, LDX>(Xs, dOb, p.sn, q0, p.N, c0, p.d);
           __syncthreads();
-          gemm_tn(acc_v[c], Ps, Xs, ty, tx);
+          zero16(part);
+          gemm_tn(part, Ps, Xs, ty, tx);
+          add_into(acc_v[c], part);
           __syncthreads();
           load_tile<64, LDX>(Xs, Qb, p.sn, q0, p.N, c0, p.d);
           __syncthreads();
-          gemm_tn(acc_k[c], Ts, Xs, ty, tx);
+          zero16(part);
+          gemm_tn(part, Ts, Xs, ty, tx);
+          add_into(acc_k[c], part);
           __syncthreads();
         }
       }
@@ -415,9 +437,12 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(AttnParams p, const T* __res
     for (int c = 0; c < NCH; ++c) {
       const int c0 = col_base + c * 64;
       if (c0 < p.d) {
+        float part[4][4];
         load_tile<64, LDX>(Xs, Kb, p.sn, k0, p.N, c0, p.d);
         __syncthreads();
-        gemm_nn(acc[c], Ts, Xs, ty, tx);
+        zero16(part);
+        gemm_nn(part, Ts, Xs, ty, tx);
+        add_into(acc[c], part);
         __syncthreads();
       }
     }

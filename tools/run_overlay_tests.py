@@ -48,6 +48,11 @@ def causal_grid(grid):
                     continue
                 if grid == "quick" and not (N == 2048 and nh <= 4 and n_embd in (64, 256, 512)):
                     continue
+                if grid == "medium":   # 21 points: every n_embd (head dims 4..1024) at N=2048, three at N=4096
+                    keep = (N == 2048 and (nh in (2, 16) or n_embd in (64, 512, 2048))) or \
+                        (N == 4096 and (nh, n_embd) in ((2, 64), (2, 512), (4, 128)))
+                    if not keep:
+                        continue
                 pts.append((nh, n_embd, N))
     return pts
 
@@ -56,6 +61,8 @@ def composed_grid(grid):
     """(nh, n_embd, N) points of the composed-branch test (use_flash_attention=False)."""
     if grid == "quick":
         return [(2, 64, 128), (4, 128, 128), (8, 256, 256)]
+    if grid == "medium":
+        return [(2, 64, 128), (4, 128, 128), (8, 256, 256), (2, 1024, 256), (8, 64, 512), (16, 256, 512)]
     return [(nh, e, N) for N in (128, 256, 512) for e in (64, 256, 1024) for nh in (2, 8)]
 
 
@@ -122,7 +129,7 @@ def run_pytest(ids, tag, log_dir, timeout=7000):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--grid", default="quick", choices=["quick", "full"])
+    ap.add_argument("--grid", default="quick", choices=["quick", "medium", "full"])
     ap.add_argument("--log", default=None)
     ap.add_argument("--skip-kernel-tests", action="store_true")
     args = ap.parse_args()
