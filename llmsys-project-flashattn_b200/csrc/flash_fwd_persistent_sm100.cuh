@@ -1,106 +1,25 @@
-// Flash-attention forward for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM.
+// PERSISTENT variant of the tcgen05 forward (flash_fwd_sm100.cuh holds the tile math, the TMEM / shared-memory layout
+// and the helpers; read that header first).  One CTA per SM walks a static list of work items (an item = 256 query
+// rows of one (batch, head)) dealt round-robin in longest-first order; the producer prefetches the next item's Q tiles
+// and the issuer puts the next item's first Q.K^T on the tensor pipe while the softmax warps are still normalising and
+// storing the current item's output.  Barrier phases are running counters; the K/V ring and the TMEM allocation live
+// across items.
 //
-// One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong so the
-// tensor pipe works on one tile while the other tile's softmax runs on the CUDA cores.
-//   warps 0-15 : four softmax groups.  Group (g, hh) = Q tile g, column half hh: thread t of warp w
-//                owns query row 32w+t of tile g (= its TMEM lane) and 2 x 32 of the 128 score columns.
-//                Two threads per row give every SM sub-partition four softmax warps to interleave
-//                (with one thread per row the phase was latency-bound at ~5 clk per instruction);
-//                the two halves agree on the row max through a 4 KB shared-memory exchange.
-//   warp 16    : TMA producer (Q tiles once; K,V tiles through an NSTAGE ring)
-//   warp 17    : tcgen05.mma issuer (one lane) + TMEM allocation
-//   warps 18-19: idle (they only complete the helper warpgroup so that setmaxnreg can move registers:
-//                20 warps launch with 96 registers each; the softmax warpgroups grow to 104, the helper
-//                warpgroup shrinks to 64)
-// TMEM (512 columns): S0 | S1 (128 fp32 columns each), O0 | O1 (D columns each).  P (bf16)
-// overwrites the first 64 columns of its S tile and is consumed directly from TMEM as the
-// A operand of the PV MMA, so P never touches shared memory.
-// Per KV tile j and Q tile g the issuer runs   O_g += P_g(j) V_j ;  S_g = Q_g K_{j+1}^T
-// and the softmax groups of g turn S_g into P_g: row max, lazy rescale of O_g (only when the max
-// grew by more than 2^8), exp2 with the 1/sqrt(d)*log2(e) scale folded into one FFMA, row sum.
-// Masks: causal (tiles above the diagonal are skipped, only the diagonal tile is masked),
-// key padding as kv_len[b] (tiles beyond it are skipped) or a generic additive (B,N) mask.
+// Where it is used (measured, profiles/r02_fwd_persistent_ab.txt): CAUSAL problems whose whole K/V fits in L2 -- the
+// short-sequence end of BASELINE config #3 -- where static longest-first balance plus the hidden prologue give +7..9 %
+// over one CTA per item.  Everywhere else the classic kernel is as fast or faster: non-causal items are equal anyway
+// (persistence measured +-1 %), and for long causal sequences the hardware's dynamic CTA scheduler over head-major
+// blocks balances better than any static deal that also keeps a head's K/V hot in L2.
 #pragma once
-#include "ptx.cuh"
+#include "flash_fwd_sm100.cuh"
 
 namespace fa {
 namespace sm100 {
 
-struct FwdParams {
-  int B, H, N;
-  const int* kv_len;      // device int32[B] or nullptr
-  const float* key_mask;  // device fp32 (B,N) or nullptr (MASKMODE 2)
-  void* O;                // (B,H,N,D) OutT with strides below
-  long long o_sb, o_sh, o_sn;
-  float* M;               // (B,H,N) row max of scaled scores
-  float* L;               // (B,H,N) sum exp(s - m)
-  float scale;            // 1/sqrt(d)
-  float scale_log2;       // scale * log2(e)
-  long long* trace;       // bring-up only (FA_TRACE builds)
-  // persistent variant only (flash_fwd_persistent_sm100.cuh)
-  int n_qblk;             // ceil(N / 256)
-  int n_items;            // n_qblk * H * B
-  int qb_major;           // item order: 0 = query blocks of one head adjacent, 1 = all heads' longest blocks first
-};
-
-#ifdef FA_TRACE
-#define FA_FTR(slot) \
-  if (tr && j < 48) tr[j * 32 + (slot)] = clock64();
-#else
-#define FA_FTR(slot)
-#endif
-
-template <int D>
-struct FwdCfg {
-  static constexpr int NCHUNK = D / 64;            // 128-byte swizzle chunks per row
-  static constexpr int CHUNK_BYTES = 128 * 128;    // [128 rows][64 bf16]
-  static constexpr int TILE_BYTES = NCHUNK * CHUNK_BYTES;
-  static constexpr int NSTAGE = (D == 128) ? 4 : 8;
-  static constexpr int SMEM_TILES = 2 * TILE_BYTES + NSTAGE * TILE_BYTES;
-  static constexpr int XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [parity][tile][half][row] fp32 row-max / row-sum exchange
-  static constexpr int SMEM_BYTES = SMEM_TILES + XCHG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
-  static constexpr int NTHREADS = 640;
-};
-
-
-template <typename OutT>
-__device__ __forceinline__ void store_row32(OutT* dst, const float* v);
-template <>
-__device__ __forceinline__ void store_row32<float>(float* dst, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-template <>
-__device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    reinterpret_cast<uint4*>(dst)[i] = u;
-  }
-}
-
-// scheduling fence: everything that produces these registers is ordered before the next volatile asm
-__device__ __forceinline__ void pin16(const uint32_t (&r)[16], float f) {
-  asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-               "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "f"(f));
-}
-
-#ifndef FA_FWD_EMU
-#define FA_FWD_EMU 1   // column PAIRS of every 8 scores whose exponentials are evaluated by the packed polynomial on the
-                       // FMA pipe (ex2_poly2) instead of MUFU.EX2.  Interleaved in-process A/B on B200 at cfg4, sustained
-                       // (power-capped) clocks, tools/ab_kernels.py: 0 -> 1.496 ms, 1 -> 1.39-1.40 ms, 2 -> 1.56 ms.
-                       // (An earlier scalar variant, 9 issue slots per exponential, was slower at every setting.)
-#endif
 // MASKMODE: 0 none (N-ragged only), 1 kv_len[b], 2 additive key mask (B,N)
 template <int D, bool CAUSAL, int MASKMODE, typename OutT>
 __global__ void __launch_bounds__(640, 1)
-    fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+    fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   using Cfg = FwdCfg<D>;
   constexpr int NSTAGE = Cfg::NSTAGE;
@@ -122,24 +41,44 @@ __global__ void __launch_bounds__(640, 1)
   uint64_t* p_lo = s_full + 2;             // [2]  P of keys [0,64) of the tile written
   uint64_t* p_hi = p_lo + 2;               // [2]  P of keys [64,128) written
   uint64_t* o_done = p_hi + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  uint64_t* q_empty = o_done + 2;          // [2]  the item's last Q.K^T of tile g has been issued and completed
+  uint64_t* o_free = q_empty + 2;          // [2]  the softmax warps have read the item's O_g out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef FA_TRACE
-  long long* tr = (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace : nullptr;
+  long long* tr = nullptr;   // (the per-iteration trace of the non-persistent kernel is not wired here)
+  const int j = 0;
+  (void)tr, (void)j;
 #endif
-  const int qb = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // causal: longest blocks first
-  const int h = blockIdx.y, b = blockIdx.z;
-  int kv_end = p.N;
-  if (MASKMODE == 1) kv_end = min(kv_end, max(__ldg(p.kv_len + b), 0));
-  const int nkv_total = (kv_end + 127) >> 7;
-  int r0[2], nkv[2];
+  const int HB = p.H * p.B;
+  // work item -> (query block, head, batch) and the number of key tiles each of its two Q tiles sees
+  struct Item {
+    int qb, h, b, kv_end, nkv[2], nk, r0[2];
+  };
+  auto decode = [&](int item) {
+    Item it;
+    int qi, bh;
+    if (p.qb_major) {
+      qi = item / HB, bh = item - qi * HB;
+    } else {
+      bh = item / p.n_qblk, qi = item - bh * p.n_qblk;
+    }
+    it.qb = CAUSAL ? (p.n_qblk - 1 - qi) : qi;   // causal: longest blocks first
+    it.h = bh % p.H;
+    it.b = bh / p.H;
+    it.kv_end = p.N;
+    if (MASKMODE == 1) it.kv_end = min(it.kv_end, max(__ldg(p.kv_len + it.b), 0));
+    const int nkv_total = (it.kv_end + 127) >> 7;
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    r0[g] = qb * 256 + g * 128;
-    nkv[g] = (r0[g] >= p.N) ? 0 : (CAUSAL ? min(nkv_total, (r0[g] >> 7) + 1) : nkv_total);
-  }
-  const int nk = max(nkv[0], nkv[1]);
+    for (int g = 0; g < 2; ++g) {
+      it.r0[g] = it.qb * 256 + g * 128;
+      it.nkv[g] = (it.r0[g] >= p.N) ? 0 : (CAUSAL ? min(nkv_total, (it.r0[g] >> 7) + 1) : nkv_total);
+    }
+    it.nk = max(it.nkv[0], it.nkv[1]);
+    return it;
+  };
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -151,6 +90,8 @@ __global__ void __launch_bounds__(640, 1)
       mbar_init(&p_lo[i], 256);
       mbar_init(&p_hi[i], 256);
       mbar_init(&o_done[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&o_free[i], 256);
     }
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -169,24 +110,32 @@ __global__ void __launch_bounds__(640, 1)
    if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      uint32_t t = 0;            // K/V tiles loaded so far (ring position), across items
+      uint32_t qn[2] = {0, 0};   // Q tiles loaded so far per slot
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode(item);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (nkv[g] > 0) {
-          mbar_expect_tx(&q_full[g], Cfg::TILE_BYTES);
+        for (int g = 0; g < 2; ++g) {
+          if (it.nkv[g] > 0) {
+            if (qn[g] > 0) mbar_wait(&q_empty[g], (qn[g] - 1) & 1);   // previous user's last Q.K^T is done
+            mbar_expect_tx(&q_full[g], Cfg::TILE_BYTES);
+#pragma unroll
+            for (int c = 0; c < Cfg::NCHUNK; ++c)
+              tma_load_4d(sQ + g * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQ, &q_full[g], c * 64, it.r0[g], it.h,
+                          it.b);
+            ++qn[g];
+          }
+        }
+        for (int u = 0; u < 2 * it.nk; ++u, ++t) {
+          const int stage = t % NSTAGE;
+          mbar_wait(&kv_empty[stage], ((t / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[stage], Cfg::TILE_BYTES);
+          const CUtensorMap* tm = (u & 1) ? &tmV : &tmK;
+          uint8_t* dst = sKV + stage * Cfg::TILE_BYTES;
 #pragma unroll
           for (int c = 0; c < Cfg::NCHUNK; ++c)
-            tma_load_4d(sQ + g * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQ, &q_full[g], c * 64, r0[g], h, b);
+            tma_load_4d(dst + c * Cfg::CHUNK_BYTES, tm, &kv_full[stage], c * 64, (u >> 1) * 128, it.h, it.b);
         }
-      }
-      for (int t = 0; t < 2 * nk; ++t) {
-        const int stage = t % NSTAGE, it = t / NSTAGE;
-        mbar_wait(&kv_empty[stage], (it & 1) ^ 1);
-        mbar_expect_tx(&kv_full[stage], Cfg::TILE_BYTES);
-        const CUtensorMap* tm = (t & 1) ? &tmV : &tmK;
-        uint8_t* dst = sKV + stage * Cfg::TILE_BYTES;
-#pragma unroll
-        for (int c = 0; c < Cfg::NCHUNK; ++c)
-          tma_load_4d(dst + c * Cfg::CHUNK_BYTES, tm, &kv_full[stage], c * 64, (t >> 1) * 128, h, b);
       }
     }
     __syncwarp();
@@ -194,7 +143,7 @@ __global__ void __launch_bounds__(640, 1)
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp walks the schedule (uniform control flow, so the descriptors live in uniform
     // registers and no per-lane serialisation loop is generated); one elected lane issues.
-    if (nk > 0) {
+    {
       const bool leader = elect_one();
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
@@ -207,12 +156,15 @@ __global__ void __launch_bounds__(640, 1)
       const uint32_t q_lo = static_cast<uint32_t>(dq), k_lo = static_cast<uint32_t>(dk),
                      v_lo = static_cast<uint32_t>(dv);
       const uint32_t kq_hi = static_cast<uint32_t>(dk >> 32), v_hi = static_cast<uint32_t>(dv >> 32);
-      auto wait_full = [&](int t) {
+      uint32_t t0 = 0;             // ring position of the current item's first K tile
+      uint32_t sn[2] = {0, 0};     // S tiles consumed so far per slot (phase of p_lo / p_hi)
+      uint32_t qn[2] = {0, 0};     // items with keys so far per slot (phase of q_full / o_free)
+      auto wait_full = [&](uint32_t t) {
         mbar_wait(&kv_full[t % NSTAGE], (t / NSTAGE) & 1);
         tc_fence_after();
       };
       // S_g = Q_g K^T : A = Q (K-major), B = K tile (K-major), 16 head-dim elements per MMA
-      auto issue_qk = [&](int g, int t) {
+      auto issue_qk = [&](int g, uint32_t t) {
         const uint32_t qa = q_lo + g * (Cfg::TILE_BYTES >> 4), ka = k_lo + (t % NSTAGE) * (Cfg::TILE_BYTES >> 4);
         if (leader) {
 #pragma unroll
@@ -224,7 +176,7 @@ __global__ void __launch_bounds__(640, 1)
       };
       // O_g += P_g V : A = P (bf16 in TMEM, 8 columns per 16 keys), B = V tile (MN-major), 16 keys per MMA
       // (issued in two halves of 64 keys so the first half overlaps the second half of the softmax)
-      auto issue_pv = [&](int g, int t, bool acc, int half) {
+      auto issue_pv = [&](int g, uint32_t t, bool acc, int half) {
         const uint32_t va = v_lo + (t % NSTAGE) * (Cfg::TILE_BYTES >> 4);
         if (leader) {
 #pragma unroll
@@ -235,47 +187,74 @@ __global__ void __launch_bounds__(640, 1)
       auto commit = [&](uint64_t* bar) {
         if (leader) mma_commit(bar);
       };
-      wait_full(0);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (nkv[g] > 0) {
-          mbar_wait(&q_full[g], 0);
-          tc_fence_after();
-          issue_qk(g, 0);
-          commit(&s_full[g]);
-        }
-      }
-      commit(&kv_empty[0]);
-      for (int j = 0; j < nk; ++j) {
-        const int tv = 2 * j + 1, tk = 2 * j + 2;
-        wait_full(tv);
-        bool k_ready = false;
+      // first Q.K^T of an item: needs the item's Q tile, and (from the second item on) the softmax warps must be
+      // done reading the previous item's O_g -- the first P.V of this item overwrites it
+      auto first_qk = [&](const Item& it) {
+        wait_full(t0);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (j < nkv[g]) {
-            mbar_wait(&p_lo[g], j & 1);
+          if (it.nkv[g] > 0) {
+            mbar_wait(&q_full[g], qn[g] & 1);
             tc_fence_after();
-            FA_FTR(0 + 4 * g)
-            issue_pv(g, tv, j > 0, 0);
-            mbar_wait(&p_hi[g], j & 1);
-            tc_fence_after();
-            issue_pv(g, tv, j > 0, 1);
-            commit(&o_done[g]);
-            FA_FTR(1 + 4 * g)
-            if (j + 1 < nkv[g]) {
-              if (!k_ready) {
-                wait_full(tk);
-                k_ready = true;
-              }
-              FA_FTR(2 + 4 * g)
-              issue_qk(g, tk);
-              commit(&s_full[g]);
-              FA_FTR(3 + 4 * g)
-            }
+            issue_qk(g, t0);
+            commit(&s_full[g]);
+            if (it.nkv[g] == 1) commit(&q_empty[g]);
           }
         }
-        commit(&kv_empty[tv % NSTAGE]);
-        if (j + 1 < nk) commit(&kv_empty[tk % NSTAGE]);
+        commit(&kv_empty[t0 % NSTAGE]);
+      };
+      // next item (at or after `from`) of this CTA that sees at least one key; n_items when there is none
+      auto next_with_keys = [&](int from, Item& out) {
+        for (; from < p.n_items; from += gridDim.x) {
+          out = decode(from);
+          if (out.nk > 0) return from;
+        }
+        return p.n_items;
+      };
+      Item it{};
+      int item = next_with_keys(blockIdx.x, it);
+      if (item < p.n_items) first_qk(it);
+      while (item < p.n_items) {
+        for (int j = 0; j < it.nk; ++j) {
+          const uint32_t tv = t0 + 2 * j + 1, tk = t0 + 2 * j + 2;
+          wait_full(tv);
+          bool k_ready = false;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (j < it.nkv[g]) {
+              if (j == 0 && qn[g] > 0) {       // O_g of the previous item has been read out by the softmax warps
+                mbar_wait(&o_free[g], (qn[g] - 1) & 1);
+                tc_fence_after();
+              }
+              mbar_wait(&p_lo[g], sn[g] & 1);
+              tc_fence_after();
+              issue_pv(g, tv, j > 0, 0);
+              mbar_wait(&p_hi[g], sn[g] & 1);
+              tc_fence_after();
+              issue_pv(g, tv, j > 0, 1);
+              commit(&o_done[g]);
+              ++sn[g];
+              if (j + 1 < it.nkv[g]) {
+                if (!k_ready) {
+                  wait_full(tk);
+                  k_ready = true;
+                }
+                issue_qk(g, tk);
+                commit(&s_full[g]);
+                if (j + 2 == it.nkv[g]) commit(&q_empty[g]);   // that was the item's last Q.K^T of this tile
+              }
+            }
+          }
+          commit(&kv_empty[tv % NSTAGE]);
+          if (j + 1 < it.nk) commit(&kv_empty[tk % NSTAGE]);
+        }
+        // the next item's first Q.K^T goes out right behind this item's last P.V: it overlaps the epilogue
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (it.nkv[g] > 0) ++qn[g];
+        t0 += 2 * it.nk;
+        item = next_with_keys(item + gridDim.x, it);
+        if (item < p.n_items) first_qk(it);
       }
     }
     __syncwarp();
@@ -289,7 +268,6 @@ __global__ void __launch_bounds__(640, 1)
     // The two warps that share 32 rows (column halves hh = 0 / 1) synchronise on their own named barrier:
     // the rescale decision below is taken per warp, so anything wider could deadlock on divergent data.
     const uint32_t pair_bar = 1 + g * 4 + w;
-    const int row = r0[g] + rl;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
     const uint32_t tSg = lane_base + (g ? Cfg::S_COL1 : Cfg::S_COL0);
     // A thread owns 2 x 32 score columns of its row: chunk A = keys [32hh, 32hh+32) and chunk B = keys
@@ -301,23 +279,33 @@ __global__ void __launch_bounds__(640, 1)
     const uint32_t tO = lane_base + (g ? Cfg::O_COL1 : Cfg::O_COL0) + (D / 2) * hh;
     const float sc = (MASKMODE == 2) ? 1.0f : p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t scnt = 0;     // S tiles of my Q-tile slot consumed so far (phase of s_full / o_done; xchg parity)
+
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const Item it = decode(item);
+    const int b = it.b, h = it.h, kv_end = it.kv_end;
+    const int nkv_g = g ? it.nkv[1] : it.nkv[0];     // (selects, not dynamic indexing: keeps Item in registers)
+    const int r0g = g ? it.r0[1] : it.r0[0];
+    const int row = r0g + rl;
     const float* mrow = (MASKMODE == 2) ? p.key_mask + static_cast<long long>(b) * p.N : nullptr;
-    OutT* orow = reinterpret_cast<OutT*>(p.O) + b * p.o_sb + h * p.o_sh + static_cast<long long>(row) * p.o_sn +
-                 (D / 2) * hh;
-    const long long stat_idx = (static_cast<long long>(b) * p.H + h) * p.N + row;
+    // (output addresses are formed where they are used, after the key loop: nothing 64-bit stays live across it)
+    auto out_row = [&]() {
+      return reinterpret_cast<OutT*>(p.O) + b * p.o_sb + h * p.o_sh + static_cast<long long>(row) * p.o_sn + (D / 2) * hh;
+    };
+    auto stat_index = [&]() { return (static_cast<long long>(b) * p.H + h) * p.N + row; };
     float* x_mine = xchg + (g * 2 + hh) * 128 + rl;        // + parity * 512
     float* x_peer = xchg + (g * 2 + (hh ^ 1)) * 128 + rl;
 
-    if (nkv[g] == 0) {
+    if (nkv_g == 0) {
       if (row < p.N) {  // no visible key at all (kv_len == 0): O = 0, m = -inf, l = 0
         float z[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) z[i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < D / 64; ++c) store_row32<OutT>(orow + 32 * c, z);
+        for (int c = 0; c < D / 64; ++c) store_row32<OutT>(out_row() + 32 * c, z);
         if (hh == 0) {
-          p.M[stat_idx] = -INFINITY;
-          p.L[stat_idx] = 0.f;
+          p.M[stat_index()] = -INFINITY;
+          p.L[stat_index()] = 0.f;
         }
       }
     } else {
@@ -332,7 +320,7 @@ __global__ void __launch_bounds__(640, 1)
             s[i] = fmaf(s[i], p.scale_log2, mv * LOG2E);
           }
         }
-        if ((key0 + 32 > kv_end) || (CAUSAL && (key0 + 31 > r0[g]))) {
+        if ((key0 + 32 > kv_end) || (CAUSAL && (key0 + 31 > r0g))) {
           int limit = kv_end - key0;
           if (CAUSAL) limit = min(limit, row - key0 + 1);
 #pragma unroll
@@ -385,10 +373,9 @@ __global__ void __launch_bounds__(640, 1)
         f32x2_unpack(add_f32x2(ra, rb), s0, s1);
         return s0 + s1;
       };
-      for (int j = 0; j < nkv[g]; ++j) {
-        mbar_wait(&s_full[g], j & 1);
+      for (int j = 0; j < nkv_g; ++j, ++scnt) {
+        mbar_wait(&s_full[g], scnt & 1);
         tc_fence_after();
-        FA_FTR(8 + 4 * wg)
         const int kA = j * 128 + 32 * hh, kB = kA + 64;
         float sA[32], sB[32];
         tmem_ld32f(tA, sA);      // both chunks in flight, one wait: 64 scores live
@@ -397,20 +384,17 @@ __global__ void __launch_bounds__(640, 1)
         mask_chunk(kA, sA);
         mask_chunk(kB, sB);
         float mx = fmaxf(max32(sA), max32(sB));
-        x_mine[(j & 1) * 512] = mx;
-        FA_FTR(9 + 4 * wg)
+        x_mine[(scnt & 1) * 512] = mx;
         // Speculate that the reference maximum m_used survives this tile (it does unless some row maximum
         // grows by more than 2^8): the chunk-A exponentials start right away on the MUFU pipe, the row-max
         // reduction above shares their shadow on the ALU pipe, and the exchange with the other half of the
         // row happens after them, when the partner has long arrived.  (j == 0 always takes the redo path.)
         float neg_m = -m_used * sc;
         uint32_t pk[16];
-        FA_FTR(28 + wg)
         float sumA = exp_pack(sA, neg_m, pk);
         pin16(pk, sumA);              // keep the speculative work ahead of the barrier
         named_bar_sync(pair_bar, 64);   // both halves hold their scores in registers (P may overwrite S) and published
-        FA_FTR(10 + 4 * wg)
-        mx = fmaxf(mx, x_peer[(j & 1) * 512]);
+        mx = fmaxf(mx, x_peer[(scnt & 1) * 512]);
         m_true = fmaxf(m_true, mx);
         // lazy rescale: only when some row of this warp grew by more than 2^8.  The partner warp of the
         // other half sees the same 32 row maxima, so both take the same decision.
@@ -423,7 +407,7 @@ __global__ void __launch_bounds__(640, 1)
             const float factor = ex2_approx((m_used - m_new) * sc);
             m_used = m_new;
             l_run *= factor;
-            mbar_wait(&o_done[g], (j - 1) & 1);
+            mbar_wait(&o_done[g], (scnt - 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < D / 16; ++c) {   // my half of the O columns, 8 at a time (rare path)
@@ -450,21 +434,19 @@ __global__ void __launch_bounds__(640, 1)
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&p_lo[g]);      // keys [0,64) of P are in TMEM: the first half of P.V may start
-        FA_FTR(24 + wg)
         asm volatile("" : "+f"(neg_m));   // chunk B's exponentials stay behind the p_lo signal
         l_run += exp_pack(sB, neg_m, pk);
         tmem_st16(tPB, pk);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&p_hi[g]);
-        FA_FTR(11 + 4 * wg)
       }
       // epilogue: combine the two halves' row sums, O / l -> global, statistics
-      const int par = nkv[g] & 1;
+      const int par = scnt & 1;
       x_mine[par * 512] = l_run;
       named_bar_sync(pair_bar, 64);
       const float l_tot = l_run + x_peer[par * 512];
-      mbar_wait(&o_done[g], (nkv[g] - 1) & 1);
+      mbar_wait(&o_done[g], (scnt - 1) & 1);
       tc_fence_after();
       const float inv = (l_tot > 0.f) ? 1.0f / l_tot : 0.f;
 #pragma unroll
@@ -472,16 +454,24 @@ __global__ void __launch_bounds__(640, 1)
         float o[32];
         tmem_ld32f(tO + 32 * c, o);
         tmem_wait_ld();
+        if (c == D / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(&o_free[g]);       // O_g is in registers: the next item's first P.V may overwrite it
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
-        if (row < p.N) store_row32<OutT>(orow + 32 * c, o);
+        if (row < p.N) store_row32<OutT>(out_row() + 32 * c, o);
       }
       if (row < p.N && hh == 0) {
         const float m_out = (MASKMODE == 2) ? m_true * (1.0f / LOG2E) : m_true * p.scale;
-        p.M[stat_idx] = m_out;
-        p.L[stat_idx] = (m_true == -INFINITY) ? 0.f : l_tot * ex2_approx((m_used - m_true) * sc);
+        p.M[stat_index()] = m_out;
+        p.L[stat_index()] = (m_true == -INFINITY) ? 0.f : l_tot * ex2_approx((m_used - m_true) * sc);
       }
+      // the exchange slot of parity `par` is reused by the next item's first tile (same parity): make sure the
+      // partner has read this item's row sum before it is overwritten
+      named_bar_sync(pair_bar, 64);
     }
+    }   // item loop
   }
   tc_fence_before();
   __syncthreads();

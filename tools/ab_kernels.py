@@ -22,7 +22,8 @@ for d in dirs:
     libs.append(lib)
 L0 = libs[0]
 d = int(os.environ.get("AB_D", "128"))
-B, H, N = 8, 32, 4096
+B, H, N = int(os.environ.get("AB_B", "8")), int(os.environ.get("AB_H", "32")), int(os.environ.get("AB_N", "4096"))
+CAUSAL, PAD = int(os.environ.get("AB_CAUSAL", "0")), int(os.environ.get("AB_PAD", "1"))
 n = B * H * N * d
 rng = np.random.default_rng(0)
 kv = rng.integers(N // 2, N + 1, B).astype(np.int32)
@@ -43,7 +44,7 @@ m, l = L0.fa_malloc(B * H * N * 4), L0.fa_malloc(B * H * N * 4)
 dkv = L0.fa_malloc(B * 4)
 L0.fa_h2d(dkv, kv.ctypes.data_as(ctypes.c_void_p), B * 4)
 a = _lib.fa_attn_desc()
-a.B, a.H, a.N, a.d, a.dtype, a.causal, a.kv_len = B, H, N, d, _lib.FA_DTYPE_BF16, 0, dkv
+a.B, a.H, a.N, a.d, a.dtype, a.causal, a.kv_len = B, H, N, d, _lib.FA_DTYPE_BF16, CAUSAL, (dkv if PAD else None)
 
 
 def run(lib):
@@ -59,7 +60,9 @@ for lib in libs:
     for _ in range(5):
         run(lib)
 L0.fa_sync()
-ROUNDS, ITERS = 12, 20
+ROUNDS, ITERS = int(os.environ.get("AB_ROUNDS", "12")), int(os.environ.get("AB_ITERS", "20"))
+flops = _lib.load("flashattention_kernel").fa_attn_flops(B, H, N, d, CAUSAL, kv.ctypes.data_as(ctypes.c_void_p) if PAD else None,
+                                                         0 if what == "fwd" else 1)
 times = [[] for _ in libs]
 for r in range(ROUNDS):
     order = list(range(len(libs)))
@@ -74,4 +77,5 @@ for r in range(ROUNDS):
         lib.fa_event_record(e1, None)
         times[i].append(lib.fa_event_elapsed_ms(e0, e1) / ITERS)
 for dname, t in zip(dirs, times):
-    print(f"{dname:24s} {what} median {np.median(t):.4f} ms  min {min(t):.4f}  max {max(t):.4f}")
+    print(f"{dname:24s} {what} B{B} H{H} N{N} d{d} causal{CAUSAL} pad{PAD}: median {np.median(t):.4f} ms  min {min(t):.4f}  "
+          f"max {max(t):.4f}  -> {flops / np.median(t) / 1e9:.0f} TFLOP/s")
