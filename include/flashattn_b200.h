@@ -222,6 +222,19 @@ int fa_reduce_dev(float* out, const int* out_shape, const int* out_strides, cons
                   const int* a_strides, int nd, int reduce_dim, double reduce_value, int fn_id, fa_stream_t stream);
 int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, const float* a, const int* a_shape,
                   const int* a_strides, const float* b, const int* b_shape, const int* b_strides, fa_stream_t stream);
+/* bf16 tensor-core GEMM for the Linear layers around the attention core (additive; the reference's
+ * MatrixMultiplyKernel, src/combine.cu:148-210, is one fp32 thread per output element):
+ *   C[M,N] (fp32, or bf16 when out_bf16) = A[M,K] . B[K,N], bf16 operands, fp32 accumulation on tcgen05.
+ *   a_mn = 0: A stored [M][lda], K contiguous;   a_mn = 1: A stored [K][lda], M contiguous (x^T of a row-major x);
+ *   b_mn = 1: B stored [K][ldb], N contiguous;   b_mn = 0: B stored [N][ldb], K contiguous (W^T of a row-major W).
+ * So y = x.W, dx = dy.W^T and dW = x^T.dy all run on the stored tensors without a transpose copy.  Pointers 16-byte
+ * aligned, lda / ldb multiples of 8 elements (FA_ERR_UNSUPPORTED otherwise: use fa_matmul_dev).
+ * fa_qkv_proj_bf16_dev: x (M,E) times the concatenated weight (E,3E) in ONE GEMM; the three column blocks land in
+ * separate (M,E) buffers = q, k, v in the (B,N,nh,d) layout fa_flash_fwd_dev consumes in place (E % 32 == 0). */
+int fa_gemm_bf16_dev(void* out, int out_bf16, long long ldo, const void* a_bf16, int a_mn, long long lda,
+                     const void* b_bf16, int b_mn, long long ldb, int M, int N, int K, fa_stream_t stream);
+int fa_qkv_proj_bf16_dev(void* q, void* k, void* v, int out_bf16, const void* x_bf16, const void* wqkv_bf16, int M, int E,
+                         fa_stream_t stream);
 /* Embedding lookup and softmax cross-entropy without one-hot matmuls (additive; the reference
  * builds (tokens, vocab) one-hot matrices, minitorch/modules_basic.py:55-71 and nn.py:251-271, and only declares
  * fused kernels, src/includes/kernels.h:196-215).  ids / targets are fp32 tensors holding integers.

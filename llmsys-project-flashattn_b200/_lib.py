@@ -120,6 +120,9 @@ SYMBOLS["combine"] = {
                          c_int, c_int]),
     "tensorReduce": (None, [_f32, _i32, _i32, c_int, _f32, _i32, _i32, c_int, c_double, c_int, c_int]),
     "MatrixMultiply": (None, [_f32, _i32, _i32, _f32, _i32, _i32, _f32, _i32, _i32, c_int, c_int, c_int]),
+    "fa_gemm_bf16_dev": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong,
+                                 c_int, c_int, c_int, c_void_p]),
+    "fa_qkv_proj_bf16_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "fa_map_dev": (c_int, [c_void_p, _i32, _i32, c_int, c_void_p, _i32, _i32, c_int, c_int, c_void_p]),
     "fa_zip_dev": (c_int, [c_void_p, _i32, _i32, c_int, c_void_p, _i32, _i32, c_int, c_void_p, _i32, _i32, c_int, c_int,
                            c_void_p]),

@@ -19,6 +19,8 @@
 #include <cstdint>
 
 #include "host_common.cuh"
+#include "tma_host.cuh"
+#include "gemm_sm100.cuh"
 
 namespace fa {
 
@@ -692,6 +694,72 @@ int fa_matmul_dev(float* out, const int* out_shape, const int* out_strides, cons
   count_launch();
   FA_CUDA_CHECK(cudaGetLastError());
   return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bf16 tensor-core GEMM (gemm_sm100.cuh): C[M,N] = A[M,K] . B[K,N], fp32 accumulation.
+//   a_mn == 0: A is [M][lda] with K contiguous;  a_mn == 1: A is stored [K][lda] with M contiguous (x^T of a row-major x)
+//   b_mn == 1: B is [K][ldb] with N contiguous;  b_mn == 0: B is stored [N][ldb] with K contiguous (W^T of a row-major W)
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace fa {
+static int launch_gemm_bf16(const gemm::Params& p, const void* a, int a_mn, long long lda, const void* b, int b_mn,
+                            long long ldb, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return set_error(FA_ERR_INVALID, "gemm: bad shape %d x %d x %d", p.M, p.N, p.K);
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
+    return set_error(FA_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned with leading dimensions that are "
+                                         "multiples of 8 elements (lda %lld, ldb %lld)", lda, ldb);
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) rc = make_tmap_2d(&ta, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.M, p.K, lda, 64, 64);
+  else rc = make_tmap_2d(&ta, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.K, p.M, lda, 64, 128);
+  if (rc) return rc;
+  if (b_mn) rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.N, p.K, ldb, 64, 64);
+  else rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.K, p.N, ldb, 64, 128);
+  if (rc) return rc;
+  dim3 grid((p.N + gemm::BN - 1) / gemm::BN, (p.M + gemm::BM - 1) / gemm::BM);
+  auto go = [&](auto kern) -> int {
+    FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    kern<<<grid, gemm::NTHREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p);
+    count_launch();
+    FA_CUDA_CHECK(cudaGetLastError());
+    return FA_OK;
+  };
+  if (a_mn && b_mn) return go(gemm::gemm_kernel<true, true>);
+  if (a_mn) return go(gemm::gemm_kernel<true, false>);
+  if (b_mn) return go(gemm::gemm_kernel<false, true>);
+  return go(gemm::gemm_kernel<false, false>);
+}
+}  // namespace fa
+extern "C" {
+
+int fa_gemm_bf16_dev(void* out, int out_bf16, long long ldo, const void* a, int a_mn, long long lda, const void* b,
+                     int b_mn, long long ldb, int M, int N, int K, fa_stream_t stream) {
+  clear_error();
+  if (!out || !a || !b) return set_error(FA_ERR_INVALID, "fa_gemm_bf16_dev: null pointer");
+  gemm::Params p{};
+  p.M = M, p.N = N, p.K = K;
+  p.out[0] = out;
+  p.n_split = 0;
+  p.ldo = ldo;
+  p.out_bf16 = out_bf16 ? 1 : 0;
+  return launch_gemm_bf16(p, a, a_mn ? 1 : 0, lda, b, b_mn ? 1 : 0, ldb, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Fused Q/K/V projection: x (M, E) bf16 row-major times the concatenated weight wqkv (E, 3E) bf16 row-major in ONE GEMM;
+// column block j goes to its own (M, E) row-major buffer -- q, k, v in the (B, N, nh, d) layout the flash kernels consume.
+int fa_qkv_proj_bf16_dev(void* q, void* k, void* v, int out_bf16, const void* x, const void* wqkv, int M, int E,
+                         fa_stream_t stream) {
+  clear_error();
+  if (!q || !k || !v || !x || !wqkv) return set_error(FA_ERR_INVALID, "fa_qkv_proj_bf16_dev: null pointer");
+  if (E <= 0 || (E & 31)) return set_error(FA_ERR_UNSUPPORTED, "fa_qkv_proj_bf16_dev: n_embd %d must be a multiple of 32", E);
+  gemm::Params p{};
+  p.M = M, p.N = 3 * E, p.K = E;
+  p.out[0] = q, p.out[1] = k, p.out[2] = v;
+  p.n_split = E;
+  p.ldo = E;
+  p.out_bf16 = out_bf16 ? 1 : 0;
+  return launch_gemm_bf16(p, x, 0, E, wqkv, 1, 3LL * E, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fa_embedding_fw_dev(float* out, const float* ids, const float* W, long long n, int V, int E, fa_stream_t stream) {

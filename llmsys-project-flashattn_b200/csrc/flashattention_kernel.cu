@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "host_common.cuh"
+#include "tma_host.cuh"
 #include "flash_fp32.cuh"
 #include "flash_fwd_sm100.cuh"
 #include "flash_fwd_persistent_sm100.cuh"
@@ -36,21 +37,6 @@ static int current_mode() {
 // TMA descriptors.  cuTensorMapEncodeTiled is fetched through the runtime so the library does
 // not link against libcuda.
 // --------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // 4-D map over a (B,H,N,d) tensor with element strides (sb, sh, sn, 1); box = [box_rows][box_cols] x 1 x 1,
 // 128-byte swizzle, out-of-bounds rows read as zero / are not written.
 static int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, int B, int H, int N, int d,

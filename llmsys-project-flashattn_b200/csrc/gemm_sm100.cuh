@@ -1,0 +1,178 @@
+// bf16 GEMM on tcgen05 for the Linear layers around the attention core:
+//     C[M, N] (fp32 or bf16, row-major) = A[M, K] . B[K, N]       bf16 operands, fp32 accumulation in TMEM
+// The reference runs every projection through src/combine.cu:148-210 (one thread per output element, fp32 FMA).
+//
+// Either operand may be given in either memory order, so the three GEMMs of a Linear layer need no transposes:
+//     forward   y  = x . W           A = x  [M][K] (K contiguous: "K-major"),   B = W  [K][N] (N contiguous: "MN-major")
+//     backward  dx = dy . W^T        A = dy [M][K'] K-major,                    B = W^T given as W [N'][K'] -> K-major
+//               dW = x^T . dy        A = x^T given as x [K'][M'] -> MN-major,   B = dy [K'][N] MN-major
+// One 128x128 output tile per CTA, K consumed 64 elements per stage through a 4-deep TMA ring (128-byte swizzled
+// tiles, the same descriptor conventions as the attention kernels: a K-major tile is [128 rows][64 k] with 32-byte
+// K steps, an MN-major tile is two [64 k][64 cols] chunks with 2048-byte K steps), tcgen05.mma issued by one lane
+// of warp 5, accumulator (128 lanes x 128 fp32 columns) read back by the four epilogue warps and stored row-wise.
+// Up to three outputs: the fused Q/K/V projection multiplies x by the concatenated [E][3E] weight once and writes the
+// three column blocks to separate (B*N, E) buffers -- the (B, N, nh, d) layout the flash kernels consume in place.
+#pragma once
+#include "ptx.cuh"
+
+namespace fa {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64, NSTAGE = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // 16 KiB each
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 192;
+
+struct Params {
+  int M, N, K;
+  void* out[3];          // column block j of width n_split goes to out[j] (n_split == 0: everything to out[0])
+  int n_split;
+  long long ldo;         // row stride of the outputs (elements)
+  int out_bf16;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  uint64_t* full = bars;                 // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
+  uint64_t* acc_full = bars + 2 * NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % NSTAGE;
+        mbar_wait(&empty[s], ((kt / NSTAGE) & 1) ^ 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = kt * BK;
+        if (A_MN) {       // memory [K][M]: two [64 k][64 m] chunks
+          tma_load_2d(sa, &tmA, &full[s], m0, k0);
+          tma_load_2d(sa + A_BYTES / 2, &tmA, &full[s], m0 + 64, k0);
+        } else {          // memory [M][K]: one [128 m][64 k] tile
+          tma_load_2d(sa, &tmA, &full[s], k0, m0);
+        }
+        if (B_MN) {       // memory [K][N]: two [64 k][64 n] chunks
+          tma_load_2d(sb, &tmB, &full[s], n0, k0);
+          tma_load_2d(sb + B_BYTES / 2, &tmB, &full[s], n0 + 64, k0);
+        } else {          // memory [N][K]: one [128 n][64 k] tile
+          tma_load_2d(sb, &tmB, &full[s], k0, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer (uniform control flow, one lane issues)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint64_t da = A_MN ? make_smem_desc(smem_u32(smem), A_BYTES / 2, 1024) : make_smem_desc(smem_u32(smem), 16, 1024);
+    const uint64_t db = B_MN ? make_smem_desc(smem_u32(smem + A_BYTES), B_BYTES / 2, 1024)
+                             : make_smem_desc(smem_u32(smem + A_BYTES), 16, 1024);
+    const uint32_t a_lo = static_cast<uint32_t>(da), a_hi = static_cast<uint32_t>(da >> 32);
+    const uint32_t b_lo = static_cast<uint32_t>(db), b_hi = static_cast<uint32_t>(db >> 32);
+    constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4, b_step = (B_MN ? 2048 : 32) >> 4;   // per 16 k elements
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % NSTAGE;
+      mbar_wait(&full[s], (kt / NSTAGE) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t so = (s * STAGE_BYTES) >> 4;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          mma_ss2(tmem_base, a_lo + so + k * a_step, a_hi, b_lo + so + k * b_step, b_hi, idesc, (kt > 0 || k > 0) ? 1u : 0u);
+        mma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (leader) mma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t u[32];
+      tmem_ld32(taddr + 32 * c, u);
+      tmem_wait_ld();
+      const int col0 = n0 + 32 * c;
+      if (row < p.M && col0 < p.N) {
+      // destination: column block j of width n_split lives in out[j]
+      int j = 0, cj = col0;
+      if (p.n_split > 0) {
+        j = col0 / p.n_split;
+        cj = col0 - j * p.n_split;
+      }
+      const int valid = min(32, p.N - col0);
+      if (p.out_bf16) {
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out[j]) + static_cast<long long>(row) * p.ldo + cj;
+        if (valid == 32 && (p.ldo & 7) == 0 && (cj & 7) == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(u[8 * i]), __uint_as_float(u[8 * i + 1]));
+            o.y = pack_bf16x2(__uint_as_float(u[8 * i + 2]), __uint_as_float(u[8 * i + 3]));
+            o.z = pack_bf16x2(__uint_as_float(u[8 * i + 4]), __uint_as_float(u[8 * i + 5]));
+            o.w = pack_bf16x2(__uint_as_float(u[8 * i + 6]), __uint_as_float(u[8 * i + 7]));
+            reinterpret_cast<uint4*>(dst)[i] = o;
+          }
+        } else {
+          for (int i = 0; i < valid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(u[i]));
+        }
+      } else {
+        float* dst = static_cast<float*>(p.out[j]) + static_cast<long long>(row) * p.ldo + cj;
+        if (valid == 32 && (p.ldo & 3) == 0 && (cj & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
+                                                            __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3]));
+        } else {
+          for (int i = 0; i < valid; ++i) dst[i] = __uint_as_float(u[i]);
+        }
+      }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem_base);
+}
+
+}  // namespace gemm
+}  // namespace fa

@@ -100,6 +100,7 @@ class DeviceKernelOps:
     cuda = True
     device_resident = True
     flash_mode = "fp32"       # "bf16": tcgen05 tensor-core kernels for head_dim 64 / 128 (operands rounded on device)
+    gemm_mode = "fp32"        # "bf16": 2-D matmuls (Linear fwd / bwd, lm_head) on the tcgen05 GEMM, fp32 accumulation
 
     # ---- storage hooks used by HostTensor ------------------------------------------------------------------
     @staticmethod
@@ -192,10 +193,68 @@ class DeviceKernelOps:
             raise IndexError(f"cannot broadcast matmul batches {a.shape} @ {b.shape}")
         out = a.zeros(tuple(ls))
         m, p = ls[-2], ls[-1]
+        if DeviceKernelOps.gemm_mode == "bf16" and nb == 1 and DeviceKernelOps._gemm_bf16(out, a, ast, b, bst, m, p, ash[2]):
+            return out
         lib_rc = lib.fa_matmul_dev(_st(out).ptr, _i32((nb, m, p)), _i32((m * p, p, 1)), _st(a).ptr, _i32(ash), _i32(ast),
                                    _st(b).ptr, _i32(bsh), _i32(bst), None)
         _lib.check(lib, lib_rc)
         return out
+
+    @staticmethod
+    def _gemm_bf16(out, a, ast, b, bst, m, p, k) -> bool:
+        """out (m, p) fp32 = a (m, k) @ b (k, p) on the tcgen05 GEMM (operands rounded to bf16 on the device, fp32
+        accumulation).  Transposed VIEWS are consumed in place (the kernel takes either memory order per operand), so
+        the backward GEMMs dx = dy @ W^T and dW = x^T @ dy of a Linear layer need no copies.  Returns False when the
+        layout does not fit (caller falls back to the fp32 CUDA-core matmul)."""
+        if len(_st(a)) != m * k or len(_st(b)) != k * p or m * p * k < (1 << 16):
+            return False
+        am, ak = ast[-2], ast[-1]
+        bk, bn = bst[-2], bst[-1]
+        if ak == 1 and am >= k:
+            a_mn, lda = 0, am
+        elif am == 1 and ak >= m:
+            a_mn, lda = 1, ak
+        else:
+            return False
+        if bn == 1 and bk >= p:
+            b_mn, ldb = 1, bk
+        elif bk == 1 and bn >= k:
+            b_mn, ldb = 0, bn
+        else:
+            return False
+        if lda % 8 or ldb % 8:
+            return False
+        lib = _lib.load("combine")
+        a16, b16 = DeviceStorage((m * k + 1) // 2), DeviceStorage((k * p + 1) // 2)
+        fl = _fa()
+        _lib.check(fl, fl.fa_cast_f32_to_bf16_dev(_st(a).ptr, a16.ptr, m * k, None))
+        _lib.check(fl, fl.fa_cast_f32_to_bf16_dev(_st(b).ptr, b16.ptr, k * p, None))
+        _lib.check(lib, lib.fa_gemm_bf16_dev(_st(out).ptr, 0, p, a16.ptr, a_mn, lda, b16.ptr, b_mn, ldb, m, p, k, None))
+        return True
+
+    @staticmethod
+    def qkv_projection(x2, wq, wk, wv):
+        """Fused Q/K/V projection: x2 (M, E) times the concatenated (E, 3E) weight in ONE tcgen05
+        GEMM whose three column blocks land in separate (M, E) fp32 buffers -- (B, N, nh, d) storage, which the flash
+        kernels consume in place through their strides.  Returns None when the shapes do not fit (caller uses three
+        matmuls)."""
+        M, E = x2.shape
+        if E % 32 or any(tuple(w.shape) != (E, E) for w in (wq, wk, wv)) or len(_st(x2)) != M * E or \
+                x2._tensor.strides != (E, 1) or any(w._tensor.strides != (E, 1) or len(_st(w)) != E * E for w in (wq, wk, wv)):
+            return None
+        lib, fl = _lib.load("combine"), _fa()
+        cat = DeviceStorage(3 * E * E)                       # [E][3E] fp32: three strided column-block copies
+        osh, ost = _i32((E, E)), _i32((3 * E, 1))
+        for j, w in enumerate((wq, wk, wv)):
+            ish, ist = _layout(w)
+            _lib.check(lib, lib.fa_map_dev(cat.ptr + j * E * 4, osh, ost, 2, _st(w).ptr, ish, ist, 2, _fn_id("id"), None))
+        w16, x16 = DeviceStorage((3 * E * E + 1) // 2), DeviceStorage((M * E + 1) // 2)
+        _lib.check(fl, fl.fa_cast_f32_to_bf16_dev(cat.ptr, w16.ptr, 3 * E * E, None))
+        _lib.check(fl, fl.fa_cast_f32_to_bf16_dev(_st(x2).ptr, x16.ptr, M * E, None))
+        outs = [x2.zeros((M, E)) for _ in range(3)]
+        _lib.check(lib, lib.fa_qkv_proj_bf16_dev(_st(outs[0]).ptr, _st(outs[1]).ptr, _st(outs[2]).ptr, 0, x16.ptr, w16.ptr,
+                                                 M, E, None))
+        return outs
 
     # ---- flash attention ---------------------------------------------------------------------------------------
     @staticmethod
@@ -434,6 +493,13 @@ class DeviceKernelOps:
     def set_flash_mode(mode: str) -> None:
         assert mode in ("fp32", "bf16")
         DeviceKernelOps.flash_mode = mode
+
+    @staticmethod
+    def set_gemm_mode(mode: str) -> None:
+        """'fp32' (default: fp32 CUDA-core matmul, <= 1e-5) or 'bf16' (tcgen05 GEMM, bf16 operands / fp32 accumulate)."""
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(mode)
+        DeviceKernelOps.gemm_mode = mode
 
     @staticmethod
     def get_flash_mode() -> str:

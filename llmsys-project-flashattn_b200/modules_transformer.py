@@ -14,7 +14,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .tensor import GELU, EmbeddingLookup, HostTensor, TensorBackend, default_backend, one_hot, softmax, tensor_from_numpy
+from .tensor import (GELU, EmbeddingLookup, HostTensor, TensorBackend, default_backend, fused_qkv, one_hot, softmax,
+                     tensor_from_numpy)
 
 datatype = np.float32
 
@@ -118,11 +119,20 @@ class MultiHeadAttention(Module):
         batch_size, seq_len, n_embd = x.shape
         x2 = x.contiguous().view(batch_size * seq_len, n_embd)
         split = (batch_size, seq_len, self.n_head, self.attn_hidden_dim)
-        q = self.q_projection(x2).view(*split).permute(0, 2, 1, 3)
-        k = self.k_projection(x2).view(*split)
+        fused = None
+        if self.q_projection.bias is None and self.k_projection.bias is None and self.v_projection.bias is None:
+            # one GEMM for all three projections when the backend has a tensor-core GEMM mode
+            fused = fused_qkv(x2, self.q_projection.weights.value, self.k_projection.weights.value,
+                              self.v_projection.weights.value)
+        if fused is not None:
+            q2, k2, v2 = fused
+        else:
+            q2, k2, v2 = self.q_projection(x2), self.k_projection(x2), self.v_projection(x2)
+        q = q2.view(*split).permute(0, 2, 1, 3)
+        k = k2.view(*split)
         kT = k.permute(0, 2, 3, 1)
         k = k.permute(0, 2, 1, 3)
-        v = self.v_projection(x2).view(*split).permute(0, 2, 1, 3)
+        v = v2.view(*split).permute(0, 2, 1, 3)
         return q, k, kT, v
 
     def self_attention(self, q: HostTensor, kT: HostTensor, v: HostTensor) -> HostTensor:

@@ -342,6 +342,34 @@ def _unbroadcast(g: HostTensor, shape) -> HostTensor:
     return g.contiguous().view(*shape)
 
 
+class QKVPart(Function):
+    """One of the three outputs of the fused Q/K/V projection: the forward of all three is ONE GEMM
+    (ops.qkv_projection, run by the first part and shared through `call`); each part is its own autograd node whose
+    backward is the Linear backward of its weight (dx = g @ W^T, dW = x^T @ g -- tensor-core GEMMs in bf16 GEMM mode)."""
+
+    @staticmethod
+    def forward(ctx, x2, w, call, j):
+        ctx.save_for_backward(x2, w)
+        return call[j]
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w = ctx.saved_values
+        g = g.contiguous()
+        return g.f.matrix_multiply(g, w.permute(1, 0)), g.f.matrix_multiply(x2.permute(1, 0), g)
+
+
+def fused_qkv(x2, wq, wk, wv):
+    """(q2, k2, v2) = x2 @ wq, x2 @ wk, x2 @ wv through one fused GEMM, or None when the backend cannot do it."""
+    ops = x2.backend.ops
+    if not hasattr(ops, "qkv_projection") or getattr(ops, "gemm_mode", "fp32") != "bf16":
+        return None
+    call = ops.qkv_projection(x2.detach(), wq.detach(), wk.detach(), wv.detach())
+    if call is None:
+        return None
+    return tuple(QKVPart.apply(x2, w, call, j) for j, w in enumerate((wq, wk, wv)))
+
+
 class MatMul(Function):
     """minitorch/tensor_functions.py:413-432."""
 
