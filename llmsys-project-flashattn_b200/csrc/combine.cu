@@ -714,21 +714,26 @@ static int launch_gemm_bf16(const gemm::Params& p, const void* a, int a_mn, long
   if (a_mn) rc = make_tmap_2d(&ta, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.M, p.K, lda, 64, 64);
   else rc = make_tmap_2d(&ta, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.K, p.M, lda, 64, 128);
   if (rc) return rc;
+  // 256-wide tiles when the output is wide enough and the split boundaries of a fused projection stay tile-aligned
+  const int bn = (p.N >= 256 && (p.n_split == 0 || p.n_split % 32 == 0)) ? 256 : 128;
   if (b_mn) rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.N, p.K, ldb, 64, 64);
-  else rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.K, p.N, ldb, 64, 128);
+  else rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.K, p.N, ldb, 64, bn);
   if (rc) return rc;
-  dim3 grid((p.N + gemm::BN - 1) / gemm::BN, (p.M + gemm::BM - 1) / gemm::BM);
-  auto go = [&](auto kern) -> int {
-    FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    kern<<<grid, gemm::NTHREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p);
+  dim3 grid((p.N + bn - 1) / bn, (p.M + gemm::BM - 1) / gemm::BM);
+  auto go = [&](auto kern, int smem) -> int {
+    FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, gemm::NTHREADS, smem, st>>>(ta, tb, p);
     count_launch();
     FA_CUDA_CHECK(cudaGetLastError());
     return FA_OK;
   };
-  if (a_mn && b_mn) return go(gemm::gemm_kernel<true, true>);
-  if (a_mn) return go(gemm::gemm_kernel<true, false>);
-  if (b_mn) return go(gemm::gemm_kernel<false, true>);
-  return go(gemm::gemm_kernel<false, false>);
+#define FA_GEMM_CASE(AM, BMN)                                                                        \
+  if ((a_mn != 0) == AM && (b_mn != 0) == BMN)                                                       \
+    return bn == 256 ? go(gemm::gemm_kernel<AM, BMN, 256>, gemm::Cfg<256>::SMEM_BYTES)              \
+                     : go(gemm::gemm_kernel<AM, BMN, 128>, gemm::Cfg<128>::SMEM_BYTES);
+  FA_GEMM_CASE(true, true) FA_GEMM_CASE(true, false) FA_GEMM_CASE(false, true) FA_GEMM_CASE(false, false)
+#undef FA_GEMM_CASE
+  return FA_ERR_INVALID;
 }
 }  // namespace fa
 extern "C" {

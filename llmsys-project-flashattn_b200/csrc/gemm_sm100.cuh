@@ -18,11 +18,17 @@
 namespace fa {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 64, NSTAGE = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // 16 KiB each
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64, NSTAGE = 4;
+constexpr int A_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int NTHREADS = 192;
+// BN = 256 halves the A-operand re-reads per output column (an M128xN128xK16 SS MMA fetches 8 KB of shared memory per
+// 64 clk = the whole 128 B/clk of the SM; N = 256 needs 12 KB per 128 clk), BN = 128 is kept for narrow outputs.
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct Params {
   int M, N, K;
@@ -40,9 +46,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  if (warp == 5) tmem_alloc<BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -86,10 +93,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         } else {          // memory [M][K]: one [128 m][64 k] tile
           tma_load_2d(sa, &tmA, &full[s], k0, m0);
         }
-        if (B_MN) {       // memory [K][N]: two [64 k][64 n] chunks
-          tma_load_2d(sb, &tmB, &full[s], n0, k0);
-          tma_load_2d(sb + B_BYTES / 2, &tmB, &full[s], n0 + 64, k0);
-        } else {          // memory [N][K]: one [128 n][64 k] tile
+        if (B_MN) {       // memory [K][N]: BN / 64 chunks of [64 k][64 n]
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, &full[s], n0 + 64 * c, k0);
+        } else {          // memory [N][K]: one [BN n][64 k] tile
           tma_load_2d(sb, &tmB, &full[s], k0, n0);
         }
       }
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const uint64_t da = A_MN ? make_smem_desc(smem_u32(smem), A_BYTES / 2, 1024) : make_smem_desc(smem_u32(smem), 16, 1024);
-    const uint64_t db = B_MN ? make_smem_desc(smem_u32(smem + A_BYTES), B_BYTES / 2, 1024)
+    const uint64_t db = B_MN ? make_smem_desc(smem_u32(smem + A_BYTES), 8192, 1024)
                              : make_smem_desc(smem_u32(smem + A_BYTES), 16, 1024);
     const uint32_t a_lo = static_cast<uint32_t>(da), a_hi = static_cast<uint32_t>(da >> 32);
     const uint32_t b_lo = static_cast<uint32_t>(db), b_hi = static_cast<uint32_t>(db >> 32);
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<128>(tmem_base);
+  if (warp == 5) tmem_dealloc<BN>(tmem_base);
 }
 
 }  // namespace gemm

@@ -19,6 +19,9 @@ from tests.test_host_modules import decoder_loss  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     residency = sys.argv[2] if len(sys.argv) > 2 else "host"      # "host": reference-style host storage; "device": HBM
+    gemm = sys.argv[3] if len(sys.argv) > 3 else "fp32"           # "bf16": Linear fwd / bwd on the tcgen05 GEMM (device only)
+    if residency == "device":
+        fb.DeviceKernelOps.set_gemm_mode(gemm)
     backend = fb.TensorBackend(fb.DeviceKernelOps) if residency == "device" else fb.default_backend()
     n_vocab, n_embd, n_head, n_pos = 10000, 256, 8, 40
     rng = np.random.default_rng(11111)
@@ -45,10 +48,11 @@ def main():
             loss[branch] = float(total.to_numpy().reshape(-1)[0])
     for branch in models:
         print(json.dumps({"workload": f"DecoderLM cfg2 step (fwd + loss + bwd), batch {B}, seq 39, fp32",
-                          "storage": residency,
+                          "storage": residency, "gemm": gemm if residency == "device" else "fp32",
                           "attention": branch, "step_s_best": min(times[branch]), "step_s_all": times[branch],
                           "loss": loss[branch]}), flush=True)
     fb.CudaKernelOps.set_flash_mode("fp32")
+    fb.DeviceKernelOps.set_gemm_mode("fp32")
 
 
 if __name__ == "__main__":
