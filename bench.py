@@ -332,6 +332,8 @@ def main():
 
     rank, world, local, dist = dist_setup(args.gpus)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    if world > 1:   # the ranks share the host's cores: split them between the ranks' staging threads (end-to-end leg)
+        os.environ.setdefault("MINITORCH_FA_COPY_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // world))))
     import flashattn_b200 as fb
     from flashattn_b200 import device as dev
     lib = fb._lib.load("flashattention_kernel")
