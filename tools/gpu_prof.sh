@@ -2,7 +2,7 @@
 # usage: gpu_prof.sh <kernel-regex> <out-name> [skip]   -- plain run first, then launch list + one full ncu capture
 mkdir -p gpurun_out
 K=$1; OUT=$2; SKIP=${3:-3}
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extras"
 timeout 600 $CMD > gpurun_out/plain_$OUT.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$OUT.csv $CMD > gpurun_out/ncul_$OUT.log 2>&1
 echo "ncu launches rc=$?"
