@@ -66,6 +66,10 @@ enum { FA_DTYPE_F32 = 0, FA_DTYPE_BF16 = 1 };
 enum { FA_MODE_FP32 = 0, FA_MODE_BF16 = 1 };
 void fa_set_mode(int mode);
 int fa_get_mode(void);
+/* bf16 backward without atomics: the tensor-core backward sums dQ across KV tiles with fp32 add-reductions in varying
+ * order (reproducible to rounding, not bitwise); on = 1 (or env MINITORCH_FA_DETERMINISTIC=1) runs the deterministic
+ * CUDA-core backward for bf16 tensors instead (much slower).  Forward and fp32 mode are always bitwise reproducible. */
+void fa_set_deterministic(int on);
 /* The legacy entry points are transfer-bound, so they cut the (batch, head) units into chunks of about this many bytes of
  * fp32 per tensor and overlap H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 on three streams (results are
  * independent of the chunking).  Default 16 MiB for direct copies / 64 MiB for staged ones, or env MINITORCH_FA_CHUNK_MB;

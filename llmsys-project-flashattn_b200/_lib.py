@@ -78,6 +78,7 @@ SYMBOLS = {
         **_COMMON,
         "fa_set_mode": (None, [c_int]),
         "fa_get_mode": (c_int, []),
+        "fa_set_deterministic": (None, [c_int]),
         "fa_set_legacy_chunk_bytes": (None, [c_size_t]),
         "fa_set_keep_forward_mb": (None, [c_longlong]),
         "fa_forward_cache_stats": (None, [POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),

@@ -25,6 +25,19 @@ namespace fa {
 static int g_mode = -1;  // resolved lazily from MINITORCH_FA_MODE
 static long long* g_trace = nullptr;  // FA_TRACE bring-up builds only
 
+// Deterministic bf16 backward: the tensor-core backward accumulates dQ across KV-tile CTAs with fp32 TMA add-reductions
+// whose order varies from run to run (results reproducible to fp32 rounding of the sum, far below one bf16 ulp, but not
+// bitwise).  With this switch (or env MINITORCH_FA_DETERMINISTIC=1) the bf16 backward runs the two-kernel CUDA-core
+// path instead (no atomics, bitwise reproducible, ~40x slower); the forward and the fp32 mode are always deterministic.
+static int g_deterministic = -1;
+static bool deterministic() {
+  if (g_deterministic < 0) {
+    const char* e = getenv("MINITORCH_FA_DETERMINISTIC");
+    g_deterministic = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_deterministic != 0;
+}
+
 static int current_mode() {
   if (g_mode < 0) {
     const char* e = getenv("MINITORCH_FA_MODE");
@@ -396,6 +409,7 @@ void fa_set_mode(int mode) {
   g_mode = (mode == FA_MODE_BF16) ? FA_MODE_BF16 : FA_MODE_FP32;
 }
 int fa_get_mode(void) { return current_mode(); }
+void fa_set_deterministic(int on) { g_deterministic = on ? 1 : 0; }
 #ifdef FA_TRACE
 void fa_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 #endif
@@ -455,7 +469,7 @@ int fa_flash_bwd_dev(const fa_attn_desc* a, const void* Q, const void* K, const 
     return set_error(FA_ERR_INVALID, "fa_flash_bwd_dev: null tensor pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->dtype == FA_DTYPE_F32) return bwd_simt<float>(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
-  if (tc_supported(a)) {
+  if (tc_supported(a) && !deterministic()) {
     int r2 = bwd_tc(a, Q, K, V, O, dO, m, l, dQ, dK, dV, st);
     if (r2 != FA_ERR_UNSUPPORTED) return r2;
     clear_error();

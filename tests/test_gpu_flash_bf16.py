@@ -131,6 +131,25 @@ def test_bf16_reproducible_to_rounding():
     assert maxabs(runs[0][1], runs[1][1]) <= 2.0 ** -7 * max(1.0, float(np.abs(runs[0][1]).max()))
 
 
+def test_bf16_deterministic_switch_is_bitwise_reproducible():
+    """fa_set_deterministic(1): the bf16 backward avoids the fp32 add-reductions -> dQ bitwise equal between runs,
+    and still within the bf16 tolerance of the oracle."""
+    lib = fb._lib.load("flashattention_kernel")
+    Q, K, V, dO = _inputs(1, 2, 384, 128, 35)
+    dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(x, "bf16") for x in (Q, K, V, dO))
+    O, m, l = dev.flash_fwd(dq, dk, dv, causal=True)
+    lib.fa_set_deterministic(1)
+    try:
+        runs = [[x.to_numpy() for x in dev.flash_bwd(dq, dk, dv, O, ddo, m, l, causal=True)] for _ in range(2)]
+    finally:
+        lib.fa_set_deterministic(0)
+    for a, b in zip(*runs):
+        np.testing.assert_array_equal(a, b)
+    for got, want in zip(runs[0], R.attention_bwd(Q, K, V, dO, causal=True)):
+        ok, err = close_bf16(got, want)
+        assert ok, err
+
+
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("d", [128, 64])
 @pytest.mark.parametrize("causal", [False, True])
