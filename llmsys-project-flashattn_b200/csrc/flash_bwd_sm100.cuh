@@ -42,6 +42,7 @@ namespace sm100 {
 
 struct BwdParams {
   int B, H, N, Npad;
+  int d;               // real head dim (<= D): columns d..D-1 are TMA zero-fill (inputs) / never stored (outputs)
   const int* kv_len;
   const float* key_mask;   // (B, N) additive mask or nullptr (template MASK2)
   const float* lse2;   // (B*H, Npad) NEGATED log2-domain LSE (an FFMA2 addend); -inf for rows >= N
@@ -104,7 +105,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 // 128-element row, so every load is a full 128-bit coalesced access.
 template <int D>
 __global__ void __launch_bounds__(256)
-    bwd_prep_tc_kernel(int B, int H, int N, int Npad, long long sb, long long sh, long long sn,
+    bwd_prep_tc_kernel(int B, int H, int N, int Npad, int d_real, long long sb, long long sh, long long sn,
                        const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
                        const float* __restrict__ M, const float* __restrict__ L, float* __restrict__ lse2,
                        float* __restrict__ dvec, float4* __restrict__ dq_acc4, long long n_acc4) {
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256)
     const int n = static_cast<int>(r % Npad);
     const long long bh = r / Npad;
     float s = 0.f;
-    if (n < N) {
+    if (n < N && sub * 8 < d_real) {
       const long long off = (bh / H) * sb + (bh % H) * sh + static_cast<long long>(n) * sn + sub * 8;
       const uint4 a = __ldg(reinterpret_cast<const uint4*>(O + off));
       const uint4 c = __ldg(reinterpret_cast<const uint4*>(dO + off));
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(640, 1)
     // every key of this tile is padding: its gradients are exactly zero
     for (int idx = threadIdx.x; idx < 128 * (D / 8); idx += blockDim.x) {
       const int r = idx / (D / 8), c = (idx % (D / 8)) * 8;
-      if (k0 + r < p.N) {
+      if (k0 + r < p.N && c < p.d) {
         const uint4 z = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(dKb + static_cast<long long>(k0 + r) * p.sn + c) = z;
         *reinterpret_cast<uint4*>(dVb + static_cast<long long>(k0 + r) * p.sn + c) = z;
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(640, 1)
           o.y = pack_bf16x2(__uint_as_float(u[8 * i + 2]) * mul, __uint_as_float(u[8 * i + 3]) * mul);
           o.z = pack_bf16x2(__uint_as_float(u[8 * i + 4]) * mul, __uint_as_float(u[8 * i + 5]) * mul);
           o.w = pack_bf16x2(__uint_as_float(u[8 * i + 6]) * mul, __uint_as_float(u[8 * i + 7]) * mul);
-          *reinterpret_cast<uint4*>(orow + 32 * c + 8 * i) = o;
+          if ((D / 2) * hh + 32 * c + 8 * i < p.d) *reinterpret_cast<uint4*>(orow + 32 * c + 8 * i) = o;
         }
       }
     }

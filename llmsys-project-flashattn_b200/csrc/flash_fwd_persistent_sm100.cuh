@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(640, 1)
 #pragma unroll
         for (int i = 0; i < 32; ++i) z[i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < D / 64; ++c) store_row32<OutT>(out_row() + 32 * c, z);
+        for (int c = 0; c < D / 64; ++c) store_row32_upto<OutT>(out_row() + 32 * c, z, p.d - (D / 2) * hh - 32 * c);
         if (hh == 0) {
           p.M[stat_index()] = -INFINITY;
           p.L[stat_index()] = 0.f;
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(640, 1)
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
-        if (row < p.N) store_row32<OutT>(out_row() + 32 * c, o);
+        if (row < p.N) store_row32_upto<OutT>(out_row() + 32 * c, o, p.d - (D / 2) * hh - 32 * c);
       }
       if (row < p.N && hh == 0) {
         const float m_out = (MASKMODE == 2) ? m_true * (1.0f / LOG2E) : m_true * p.scale;

@@ -28,6 +28,7 @@ namespace sm100 {
 
 struct FwdParams {
   int B, H, N;
+  int d;                  // real head dim (<= D): columns d..D-1 of every tile are TMA zero-fill and are never stored
   const int* kv_len;      // device int32[B] or nullptr
   const float* key_mask;  // device fp32 (B,N) or nullptr (MASKMODE 2)
   void* O;                // (B,H,N,D) OutT with strides below
@@ -82,6 +83,16 @@ __device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, c
     u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
     u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
     reinterpret_cast<uint4*>(dst)[i] = u;
+  }
+}
+
+// 32 output columns of one row, of which the first `valid` (a multiple of 8, possibly 0) exist (head dims below D)
+template <typename OutT>
+__device__ __forceinline__ void store_row32_upto(OutT* dst, const float* v, int valid) {
+  if (valid >= 32) {
+    store_row32<OutT>(dst, v);
+  } else {
+    for (int i = 0; i < valid; ++i) dst[i] = static_cast<OutT>(v[i]);
   }
 }
 
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(640, 1)
 #pragma unroll
         for (int i = 0; i < 32; ++i) z[i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < D / 64; ++c) store_row32<OutT>(orow + 32 * c, z);
+        for (int c = 0; c < D / 64; ++c) store_row32_upto<OutT>(orow + 32 * c, z, p.d - (D / 2) * hh - 32 * c);
         if (hh == 0) {
           p.M[stat_idx] = -INFINITY;
           p.L[stat_idx] = 0.f;
@@ -474,7 +485,7 @@ __global__ void __launch_bounds__(640, 1)
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
-        if (row < p.N) store_row32<OutT>(orow + 32 * c, o);
+        if (row < p.N) store_row32_upto<OutT>(orow + 32 * c, o, p.d - (D / 2) * hh - 32 * c);
       }
       if (row < p.N && hh == 0) {
         const float m_out = (MASKMODE == 2) ? m_true * (1.0f / LOG2E) : m_true * p.scale;

@@ -100,9 +100,13 @@ static AttnParams make_params(const fa_attn_desc* a) {
   return p;
 }
 
+// Head dims the tcgen05 kernels cover: every multiple of 8 up to 128.  The kernels are built for D = 64 and D = 128;
+// a smaller head dim runs on the next template size with its tiles zero-padded by TMA (the box is D columns wide, the
+// tensor only d: out-of-bounds columns arrive as zeros and contribute nothing to Q.K^T / P.V) and its outputs stored
+// only up to d.  BASELINE config #2's model (head_dim 32) therefore runs on tensor cores too, at D = 64 cost.
 static bool tc_supported(const fa_attn_desc* a) {
   if (a->dtype != FA_DTYPE_BF16) return false;
-  if (a->d != 64 && a->d != 128) return false;
+  if (a->d < 8 || a->d > 128 || (a->d % 8) != 0) return false;
   Strides s = resolve_strides(a);
   return (s.sn % 8 == 0) && (s.sh % 8 == 0) && (s.sb % 8 == 0);  // TMA strides: multiples of 16 bytes
 }
@@ -247,6 +251,7 @@ static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
     return rc;
   sm100::FwdParams fp;
   fp.B = a->B, fp.H = a->H, fp.N = a->N;
+  fp.d = a->d;
   fp.kv_len = a->kv_len;
   fp.key_mask = a->key_mask;
   fp.O = O;
@@ -260,8 +265,9 @@ static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   if (items > 0x7fffffffLL) return set_error(FA_ERR_UNSUPPORTED, "flash fwd: too many work items");
   fp.n_items = (int)items;
   const int maskmode = a->key_mask ? 2 : (a->kv_len ? 1 : 0);
+  const int DT = a->d <= 64 ? 64 : 128;   // template head dim
 #define FA_FWD_CASE(DD, CC, MM) \
-  if (a->d == DD && (a->causal != 0) == CC && maskmode == MM) return launch_fwd_tc<DD, CC, MM, OutT>(a, tq, tk, tv, fp, st);
+  if (DT == DD && (a->causal != 0) == CC && maskmode == MM) return launch_fwd_tc<DD, CC, MM, OutT>(a, tq, tk, tv, fp, st);
   FA_FWD_CASE(128, false, 0) FA_FWD_CASE(128, true, 0) FA_FWD_CASE(128, false, 1) FA_FWD_CASE(128, true, 1)
   FA_FWD_CASE(128, false, 2) FA_FWD_CASE(128, true, 2) FA_FWD_CASE(64, false, 0) FA_FWD_CASE(64, true, 0)
   FA_FWD_CASE(64, false, 1) FA_FWD_CASE(64, true, 1) FA_FWD_CASE(64, false, 2) FA_FWD_CASE(64, true, 2)
@@ -306,12 +312,12 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   {
     const long long blocks = 148 * 8;
     const long long n_acc4 = (long long)(nacc / 4);
-    if (a->d == 128)
-      sm100::bwd_prep_tc_kernel<128><<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, s.sb, s.sh, s.sn,
+    if (a->d > 64)
+      sm100::bwd_prep_tc_kernel<128><<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, a->d, s.sb, s.sh, s.sn,
                                                                  (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, m,
                                                                  l, lse2, dvec, (float4*)acc, n_acc4);
     else
-      sm100::bwd_prep_tc_kernel<64><<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, s.sb, s.sh, s.sn,
+      sm100::bwd_prep_tc_kernel<64><<<(int)blocks, 256, 0, st>>>(a->B, a->H, a->N, Npad, a->d, s.sb, s.sh, s.sn,
                                                                 (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, m,
                                                                 l, lse2, dvec, (float4*)acc, n_acc4);
     fa::count_launch();
@@ -332,6 +338,7 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
     return rc;
   sm100::BwdParams bp;
   bp.B = a->B, bp.H = a->H, bp.N = a->N, bp.Npad = Npad;
+  bp.d = a->d;
   bp.kv_len = a->kv_len;
   bp.key_mask = a->key_mask;
   bp.lse2 = lse2, bp.dvec = dvec, bp.dq_acc = acc;
@@ -341,8 +348,9 @@ static int bwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const voi
   bp.scale_log2 = bp.scale * 1.4426950408889634f;
   bp.trace = g_trace;
   rc = FA_ERR_UNSUPPORTED;
+  const int DT = a->d <= 64 ? 64 : 128;   // template head dim (see tc_supported)
 #define FA_BWD_CASE(DD, CC, MM)                                                       \
-  if (a->d == DD && (a->causal != 0) == CC && (a->key_mask != nullptr) == MM)         \
+  if (DT == DD && (a->causal != 0) == CC && (a->key_mask != nullptr) == MM)           \
     rc = launch_bwd_tc<DD, CC, MM>(a, tq, tk, tv, tdo, tdq, bp, st);
   FA_BWD_CASE(128, false, false) FA_BWD_CASE(128, true, false) FA_BWD_CASE(128, false, true) FA_BWD_CASE(128, true, true)
   FA_BWD_CASE(64, false, false) FA_BWD_CASE(64, true, false) FA_BWD_CASE(64, false, true) FA_BWD_CASE(64, true, true)
@@ -563,7 +571,7 @@ int fa_flash_decode_dev(const fa_decode_desc* a, const void* q, const void* k_ca
 }  // extern "C" (device-pointer API above; the legacy host-pointer ABI follows)
 
 namespace fa {
-static bool tc_head_dim(int d) { return d == 64 || d == 128; }
+static bool tc_head_dim(int d) { return d >= 8 && d <= 128 && d % 8 == 0; }
 static int fwd_tc_bf16(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, float* m, float* l,
                        cudaStream_t st) {
   Strides s = resolve_strides(a);

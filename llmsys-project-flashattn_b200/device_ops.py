@@ -308,7 +308,7 @@ class DeviceKernelOps:
         else:
             O = DeviceKernelOps._like(Q, Q._tensor.strides)
         m, l = Q.zeros((B, nh, N)), Q.zeros((B, nh, N))
-        bf16 = DeviceKernelOps.flash_mode == "bf16" and d in (64, 128)
+        bf16 = DeviceKernelOps.flash_mode == "bf16" and d % 8 == 0 and 8 <= d <= 128
         a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16, lay)
         if bf16:
             q, k, v = (_bf16_copy(t) for t in (Q, K, V))
@@ -331,7 +331,7 @@ class DeviceKernelOps:
             grads = tuple(Q.zeros((B, nh, N, d)) for _ in range(3))
         else:
             grads = tuple(DeviceKernelOps._like(Q, Q._tensor.strides) for _ in range(3))
-        bf16 = DeviceKernelOps.flash_mode == "bf16" and d in (64, 128)
+        bf16 = DeviceKernelOps.flash_mode == "bf16" and d % 8 == 0 and 8 <= d <= 128
         a = DeviceKernelOps._desc(B, nh, N, d, causal, bf16, lay)
         if bf16:
             q, k, v, o, do = (_bf16_copy(t) for t in (Q, K, V, O, dO))

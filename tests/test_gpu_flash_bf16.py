@@ -27,12 +27,12 @@ def _inputs(B, H, N, d, seed):
     return [R.round_bf16(rng.standard_normal((B, H, N, d)).astype(np.float32)) for _ in range(4)]
 
 
-def _check(B, H, N, d, causal, kv=None, mask=False, seed=0, bwd=True):
+def _check(B, H, N, d, causal, kv=None, mask=False, seed=0, bwd=True, min_valid=1):
     Q, K, V, dO = _inputs(B, H, N, d, seed)
     kv_len = np.asarray(kv, dtype=np.int32) if kv is not None else None
     km = None
     if mask:
-        valid = np.random.default_rng(seed + 1).integers(1, N + 1, B)
+        valid = np.random.default_rng(seed + 1).integers(min_valid, N + 1, B)
         km = np.where(np.arange(N)[None, :] < valid[:, None], 0.0, -1e8).astype(np.float32)
     dq, dk, dv, ddo = (dev.DeviceArray.from_numpy(x, "bf16") for x in (Q, K, V, dO))
     dkv = dev.DeviceArray.from_numpy(kv_len) if kv_len is not None else None
@@ -68,9 +68,23 @@ def test_bf16_additive_key_mask(causal):
     _check(2, 2, 384, 128, causal, mask=True, seed=9)
 
 
-def test_bf16_tiny_and_odd_head_dim_route_to_cuda_cores():
-    _check(1, 2, 39, 32, True, seed=1)   # config #2 shape: d=32 is not tiled by the tcgen05 kernels
+@pytest.mark.parametrize("d", [8, 16, 32, 48, 96, 120])
+@pytest.mark.parametrize("causal", [False, True])
+def test_bf16_head_dims_below_the_template_size(d, causal):
+    """Every head dim that is a multiple of 8 up to 128 runs on the tensor-core kernels: the tiles of the next template
+    size (64 / 128) are zero-padded by TMA and the outputs stored only up to d (BASELINE config #2's model has d = 32).
+    Masks and ragged N included."""
+    _check(2, 3, 300, d, causal, seed=d)
+    _check(2, 2, 200, d, causal, kv=[200, 37], seed=d + 1)
+    # (at least half of the keys valid: with 3 valid keys of 160, |dK| reaches 7 and the bf16 rounding of dS alone --
+    # emulated on the CPU for this seed -- moves it by 0.04, past 2e-2 + one ulp; that regime is test_bf16_kv_len's)
+    _check(2, 1, 160, d, causal, mask=True, seed=d + 2, min_valid=80)
+
+
+def test_bf16_tiny_and_odd_head_dim():
+    _check(1, 2, 39, 32, True, seed=1)   # config #2 shape (tensor-core path, TMA-padded to D = 64)
     _check(1, 1, 5, 128, False, seed=2)  # N far below one tile
+    _check(1, 2, 70, 20, True, seed=3)   # head dim that is not a multiple of 8: CUDA-core kernels
 
 
 def test_bf16_seq4096_headline_shape():
