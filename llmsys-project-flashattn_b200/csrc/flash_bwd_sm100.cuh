@@ -65,6 +65,11 @@ struct BwdParams {
 #define FA_TRW(slot)
 #endif
 
+#ifndef FA_BWD_DK_TS
+#define FA_BWD_DK_TS 0   // 1: dS^T (bf16) is also written over the thread's own dP^T columns in TMEM and the dK GEMM takes
+                         // its A operand from there (TS) instead of shared memory: -256 MMA-operand wavefronts per tile pair,
+                         // at the price of issuing dK before dQ (dQ overwrites those columns)
+#endif
 #ifndef FA_BWD_DQ_RED
 #define FA_BWD_DQ_RED 0   // 0: dQ through shared-memory staging + TMA add-reduce; 1 / 2: red.global.v4 from registers
 #endif
@@ -370,6 +375,20 @@ __global__ void __launch_bounds__(640, 1)
           mbar_wait(&ds_full[s], ph);
           tc_fence_after();
           FA_TR(4)
+#if FA_BWD_DK_TS
+          if (leader) {
+            // dK += dS^T Q_i : A = dS^T straight from TMEM (bf16 over the dP^T columns, same packing as P^T), B = Q_i
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              mma_ts2(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, mQ + k * (2048 >> 4), mn_hi, idesc_kn,
+                      (it > 0 || k > 0) ? 1u : 0u);
+            // dQ_i = dS K : overwrites T_dP (the tensor pipe runs in issue order: dK has read dS^T by then)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              mma_ss2(tdP, mDS + k * (2048 >> 4), mn_hi, mK + k * (2048 >> 4), mn_hi, idesc_mn, k > 0);
+          }
+          commit(&dq_full[s]);
+#else
           if (leader) {
             // dQ_i = dS K : A = dS^T tile read MN-major ([K=key][M=q]), B = K tile as [K=key][N=d]
 #pragma unroll
@@ -384,6 +403,7 @@ __global__ void __launch_bounds__(640, 1)
               mma_ss2(tdK, kDS + (((k >> 2) * Cfg::CHUNK_BYTES + (k & 3) * 32) >> 4), km_hi, mQ + k * (2048 >> 4),
                       mn_hi, idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
           }
+#endif
           commit(&ds_empty[s]);
           commit(&q_empty[s]);
           FA_TR(5)
@@ -539,8 +559,16 @@ __global__ void __launch_bounds__(640, 1)
                                                                __uint_as_float(u[8 * v8 + 7]) - db.w));
           const int unit = 2 * c + v8;  // 16-byte unit inside my 128-byte row
           *reinterpret_cast<uint4*>(ds_row + ((unit ^ jx) << 4)) = o;
+#if FA_BWD_DK_TS
+          pk[8 * c + 4 * v8 + 0] = o.x, pk[8 * c + 4 * v8 + 1] = o.y;   // P^T of these queries is consumed: keep dS^T
+          pk[8 * c + 4 * v8 + 2] = o.z, pk[8 * c + 4 * v8 + 3] = o.w;
+#endif
         }
       }
+#if FA_BWD_DK_TS
+      tmem_st32(tdP, pk);          // dS^T (bf16) over my own dP^T columns [64hh, 64hh+32): A operand of the dK GEMM
+      tmem_wait_st();
+#endif
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[g]);
