@@ -719,7 +719,14 @@ static int launch_gemm_bf16(const gemm::Params& p, const void* a, int a_mn, long
   if (b_mn) rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.N, p.K, ldb, 64, 64);
   else rc = make_tmap_2d(&tb, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.K, p.N, ldb, 64, bn);
   if (rc) return rc;
-  dim3 grid((p.N + bn - 1) / bn, (p.M + gemm::BM - 1) / gemm::BM);
+  const long long n_tiles = (long long)((p.N + bn - 1) / bn) * ((p.M + gemm::BM - 1) / gemm::BM);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);    // persistent: one CTA per SM walks the tiles
   auto go = [&](auto kern, int smem) -> int {
     FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, gemm::NTHREADS, smem, st>>>(ta, tb, p);

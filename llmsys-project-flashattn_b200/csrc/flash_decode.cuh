@@ -92,35 +92,66 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int x = 0; x < VN; ++x) o[i][x] = 0.f;
   const T* kb = kc + b * p.c_sb + h * p.c_sh;
   const T* vb = vc + b * p.c_sb + h * p.c_sh;
-  for (int n0 = k_begin + warp * KPW; n0 < k_end; n0 += kWarps * KPW) {
-    const int n = n0 + grp;
-    const bool ok = n < k_end;
-    float s = 0.f;
-    float kv_[NV][VN];
-    if (ok) {
+  // UNR keys per lane group and step: their K and V vectors are all requested before any arithmetic, so a lane keeps
+  // 2 * UNR * NV 16-byte loads in flight (with one key per step the kernel ran at 0.55 of the HBM peak: latency-bound)
+  constexpr int UNR = (NV == 1) ? 4 : 2;
+  for (int n0 = k_begin + warp * KPW * UNR; n0 < k_end; n0 += kWarps * KPW * UNR) {
+    float kv_[UNR][NV][VN], vv_[UNR][NV][VN];
+    bool ok[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int n = n0 + u * KPW + grp;
+      ok[u] = n < k_end;
+      const long long roff = static_cast<long long>(ok[u] ? n : k_begin) * p.c_sn;   // (clamped: the load stays in bounds)
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (live[i]) {
-          Vec<T>::load(kb + static_cast<long long>(n) * p.c_sn + (sub + i * LPK) * VN, kv_[i]);
-#pragma unroll
-          for (int x = 0; x < VN; ++x) s = fmaf(qv[i][x], kv_[i][x], s);
+          Vec<T>::load(kb + roff + (sub + i * LPK) * VN, kv_[u][i]);
+          Vec<T>::load(vb + roff + (sub + i * LPK) * VN, vv_[u][i]);
         }
     }
+    float s[UNR];
 #pragma unroll
-    for (int off = LPK / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (ok) {
-      s *= p.scale_log2;
-      const float m_new = fmaxf(m, s);
-      const float corr = exp2f(m - m_new), pr = exp2f(s - m_new);
-      m = m_new;
-      l = l * corr + pr;
+    for (int u = 0; u < UNR; ++u) {
+      s[u] = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (live[i]) {
-          Vec<T>::load(vb + static_cast<long long>(n) * p.c_sn + (sub + i * LPK) * VN, kv_[i]);
+        if (live[i])
 #pragma unroll
-          for (int x = 0; x < VN; ++x) o[i][x] = fmaf(pr, kv_[i][x], o[i][x] * corr);
-        }
+          for (int x = 0; x < VN; ++x) s[u] = fmaf(qv[i][x], kv_[u][i][x], s[u]);
+    }
+#pragma unroll
+    for (int off = LPK / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+    // online softmax over the (up to) UNR new scores at once
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (ok[u]) {
+        s[u] *= p.scale_log2;
+        m_new = fmaxf(m_new, s[u]);
+      }
+    if (m_new != -INFINITY) {
+      const float corr = exp2f(m - m_new);    // m == -inf on the first key: exp2(-inf) = 0
+      float pr[UNR], psum = 0.f;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        pr[u] = ok[u] ? exp2f(s[u] - m_new) : 0.f;
+        psum += pr[u];
+      }
+      m = m_new;
+      l = l * corr + psum;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (live[i])
+#pragma unroll
+          for (int x = 0; x < VN; ++x) {
+            float acc = o[i][x] * corr;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) acc = fmaf(pr[u], vv_[u][i][x], acc);
+            o[i][x] = acc;
+          }
     }
   }
   // merge the lane groups of this warp (lanes with equal `sub` hold the same slice of d)
