@@ -20,8 +20,10 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     residency = sys.argv[2] if len(sys.argv) > 2 else "host"      # "host": reference-style host storage; "device": HBM
     gemm = sys.argv[3] if len(sys.argv) > 3 else "fp32"           # "bf16": Linear fwd / bwd on the tcgen05 GEMM (device only)
+    flash = sys.argv[4] if len(sys.argv) > 4 else "fp32"          # "bf16": tcgen05 attention kernels (head dim 32 -> D = 64 tiles)
     if residency == "device":
         fb.DeviceKernelOps.set_gemm_mode(gemm)
+        fb.DeviceKernelOps.set_flash_mode(flash)
     backend = fb.TensorBackend(fb.DeviceKernelOps) if residency == "device" else fb.default_backend()
     n_vocab, n_embd, n_head, n_pos = 10000, 256, 8, 40
     rng = np.random.default_rng(11111)
@@ -49,10 +51,12 @@ def main():
     for branch in models:
         print(json.dumps({"workload": f"DecoderLM cfg2 step (fwd + loss + bwd), batch {B}, seq 39, fp32",
                           "storage": residency, "gemm": gemm if residency == "device" else "fp32",
+                          "flash_mode": flash if residency == "device" else "fp32",
                           "attention": branch, "step_s_best": min(times[branch]), "step_s_all": times[branch],
                           "loss": loss[branch]}), flush=True)
     fb.CudaKernelOps.set_flash_mode("fp32")
     fb.DeviceKernelOps.set_gemm_mode("fp32")
+    fb.DeviceKernelOps.set_flash_mode("fp32")
 
 
 if __name__ == "__main__":

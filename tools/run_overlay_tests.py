@@ -43,7 +43,7 @@ def causal_grid(grid):
         for n_embd in (64, 128, 256, 512, 1024, 2048):
             for nh in (2, 4, 8, 16):
                 # torch keeps ~3 live fp32 copies of the (64*nh, N, N) weights plus a transient fourth in backward
-                need = 64 * nh * N * N * 16 + 12 * 64 * N * n_embd * 4
+                need = 64 * nh * N * N * 16 + 40 * 64 * N * n_embd * 4
                 if need > 0.6 * avail:
                     continue
                 if grid == "quick" and not (N == 2048 and nh <= 4 and n_embd in (64, 256, 512)):
@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--grid", default="quick", choices=["quick", "medium", "full"])
     ap.add_argument("--log", default=None)
     ap.add_argument("--skip-kernel-tests", action="store_true")
+    ap.add_argument("--points", default=None, help="explicit causal-flash points 'nh,n_embd,N;nh,n_embd,N;...'")
     args = ap.parse_args()
     if not os.path.isdir(os.path.join(OVERLAY, "minitorch")):
         print(json.dumps(dict(error="overlay missing: run baseline/build_overlay.sh in the build container")))
@@ -147,6 +148,8 @@ def main():
             print(json.dumps(r), flush=True)
     base = "tests/test_flash_attention.py::test_multihead_attention_flash_attention"
     pts = causal_grid(args.grid)
+    if args.points:
+        pts = [tuple(int(x) for x in p.split(",")) for p in args.points.split(";")]
     ids = [f"{base}_is_causal[CudaKernelOps-0.0-{nh}-{e}-{N}-64]" for nh, e, N in pts]
     r = run_pytest(ids, "flash_causal", args.log)
     r["grid"] = [list(p) for p in pts]
