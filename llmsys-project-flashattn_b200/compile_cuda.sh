@@ -10,9 +10,13 @@ OUT="$HERE/minitorch/cuda_kernels"
 mkdir -p "$OUT"
 NVCC="${NVCC:-nvcc}"
 FLAGS=(-std=c++20 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo --shared -Xcompiler -fPIC "$@")
+# host-side fp32 <-> bf16 conversion of the legacy ABI's staging threads (plain C++, AVX2 chosen at run time)
+"${CXX:-g++}" -O3 -std=c++17 -fPIC -c "$HERE/csrc/host_convert.cpp" -o "$OUT/host_convert.o"
 pids=()
 for name in flashattention_kernel softmax_kernel layernorm_kernel combine; do
-  "$NVCC" "${FLAGS[@]}" -o "$OUT/$name.so" "$HERE/csrc/$name.cu" &
+  extra=()
+  [ "$name" = flashattention_kernel ] && extra=("$OUT/host_convert.o")
+  "$NVCC" "${FLAGS[@]}" -o "$OUT/$name.so" "$HERE/csrc/$name.cu" "${extra[@]}" &
   pids+=($!)
 done
 rc=0

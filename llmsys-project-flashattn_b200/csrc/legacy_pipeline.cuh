@@ -12,6 +12,7 @@
 //   * all per-device state (streams, events, pinned rings) is indexed by device, created once and reused.
 // Included by flashattention_kernel.cu only.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -104,16 +105,15 @@ class HostWorkers {
 enum { WIRE_F32 = 0, WIRE_BF16 = 1 };
 static inline size_t wire_bytes(int wire) { return wire == WIRE_BF16 ? 2 : 4; }
 
-// fp32 -> bf16 round-to-nearest-even (NaN stays NaN), the same rounding as cvt.rn.bf16.f32 on the device
-static inline uint16_t f32_to_bf16_bits(uint32_t u) {
-  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);
-  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+// fp32 <-> bf16 on the host (host_convert.cpp: AVX2 when the CPU has it, scalar otherwise; round to nearest even, NaN
+// stays NaN -- the same rounding as cvt.rn.bf16.f32 on the device)
+extern "C" void fa_host_narrow_f32_bf16(uint16_t* dst, const float* src, size_t n);
+extern "C" void fa_host_widen_bf16_f32(float* dst, const uint16_t* src, size_t n);
+static void narrow_piece(uint16_t* dst, const uint32_t* src, size_t n) {
+  fa_host_narrow_f32_bf16(dst, reinterpret_cast<const float*>(src), n);
 }
-static void narrow_piece(uint16_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
-  for (size_t i = 0; i < n; ++i) dst[i] = f32_to_bf16_bits(src[i]);
-}
-static void widen_piece(uint32_t* __restrict__ dst, const uint16_t* __restrict__ src, size_t n) {
-  for (size_t i = 0; i < n; ++i) dst[i] = static_cast<uint32_t>(src[i]) << 16;
+static void widen_piece(uint32_t* dst, const uint16_t* src, size_t n) {
+  fa_host_widen_bf16_f32(reinterpret_cast<float*>(dst), src, n);
 }
 static constexpr size_t kPieceElems = (size_t)1 << 19;   // 2 MiB of fp32 per work item
 // caller fp32 -> staging (plain copy or narrowing), spread over the host workers
@@ -381,6 +381,164 @@ struct LegacyShape {
 static int fwd_tc_bf16(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, float* m, float* l,
                        cudaStream_t st);   // defined in flashattention_kernel.cu
 
+// ------------------------------------------------------------------------------------------------ per-tensor transfers
+// How one caller tensor crosses PCIe is decided per tensor:
+//   * page-locked caller memory  -> DIRECT: the DMA engine reads / writes the caller's fp32 buffer itself (no CPU pass, the
+//     least host-memory traffic -- what matters when several ranks share one host); in bf16 mode the fp32 image is
+//     narrowed / widened ON THE DEVICE by a cast kernel on the compute stream;
+//   * pageable caller memory (numpy storage) -> STAGED through the pinned ring by the host threads, which narrow to bf16
+//     (bf16 mode) while they copy: a pageable buffer has to be touched by the CPU once anyway, and bf16 halves what the
+//     DMA engine then moves.
+// Tiny tensors always go direct (pageable cudaMemcpyAsync is fine below a few hundred KiB).
+struct Xfer {
+  float* host = nullptr;      // caller buffer (fp32)
+  char* dev = nullptr;        // device tensor in the kernels' dtype (wire dtype: bf16 or fp32)
+  float* dev32 = nullptr;     // device fp32 image for DIRECT transfers in bf16 mode (nullptr otherwise)
+  bool direct = true;
+  size_t unit = 0;            // elements per (batch, head) unit: N*d, or N for the statistics
+  int wire = WIRE_F32;        // dtype of `dev`
+};
+static bool use_direct(const void* host, size_t total_bytes) { return total_bytes < ((size_t)256 << 10) || !is_pageable(host); }
+
+// host -> device for the units [u0, u0 + nu) of tensor x (async on P.in; `stage` = this tensor's area of the ring slot)
+static cudaError_t xfer_in(DevPipe& P, const Xfer& x, size_t u0, size_t nu, char* stage) {
+  const size_t off = u0 * x.unit, cnt = nu * x.unit;
+  if (x.direct) {
+    void* dst = x.dev32 ? static_cast<void*>(x.dev32 + off) : static_cast<void*>(x.dev + off * 4);
+    return cudaMemcpyAsync(dst, x.host + off, cnt * 4, cudaMemcpyHostToDevice, P.in);
+  }
+  stage_in(stage, x.host + off, cnt, x.wire);
+  return cudaMemcpyAsync(x.dev + off * wire_bytes(x.wire), stage, cnt * wire_bytes(x.wire), cudaMemcpyHostToDevice, P.in);
+}
+// device-side narrowing of a DIRECT fp32 upload (compute stream, before the kernels of the chunk)
+static int xfer_in_cast(const Xfer& x, size_t u0, size_t nu, cudaStream_t comp) {
+  if (!x.dev32) return FA_OK;
+  const size_t off = u0 * x.unit, cnt = nu * x.unit;
+  return fa_cast_f32_to_bf16_dev(x.dev32 + off, x.dev + off * 2, cnt, reinterpret_cast<fa_stream_t>(comp));
+}
+// device-side widening of a result that will be downloaded DIRECTLY (compute stream, after the kernels of the chunk)
+static int xfer_out_cast(const Xfer& x, size_t u0, size_t nu, cudaStream_t comp) {
+  if (!x.dev32) return FA_OK;
+  const size_t off = u0 * x.unit, cnt = nu * x.unit;
+  return fa_cast_bf16_to_f32_dev(x.dev + off * 2, x.dev32 + off, cnt, reinterpret_cast<fa_stream_t>(comp));
+}
+// device -> host (async on P.out); a staged tensor lands in the ring slot and is handed to the caller by drain()
+static cudaError_t xfer_out(DevPipe& P, const Xfer& x, size_t u0, size_t nu, char* stage, int slot) {
+  const size_t off = u0 * x.unit, cnt = nu * x.unit;
+  if (x.direct) {
+    const void* src = x.dev32 ? static_cast<const void*>(x.dev32 + off) : static_cast<const void*>(x.dev + off * 4);
+    return cudaMemcpyAsync(x.host + off, src, cnt * 4, cudaMemcpyDeviceToHost, P.out);
+  }
+  const cudaError_t e = cudaMemcpyAsync(stage, x.dev + off * wire_bytes(x.wire), cnt * wire_bytes(x.wire),
+                                        cudaMemcpyDeviceToHost, P.out);
+  P.rout.pending[slot].push_back({x.host + off, stage, cnt, x.wire});
+  return e;
+}
+
+struct LegacyCall {
+  DevPipe* P = nullptr;
+  int dev = 0;
+  std::vector<void*> temps;      // stream-ordered device allocations of this call
+  cudaError_t e = cudaSuccess;
+  void step(cudaError_t x) {
+    if (e == cudaSuccess) e = x;
+  }
+  void* temp(size_t bytes) {
+    void* p = alloc_async(bytes, P->in, dev);
+    if (p) temps.push_back(p);
+    return p;
+  }
+  void free_temps(cudaStream_t st) {
+    for (void* p : temps) cudaFreeAsync(p, st);
+    temps.clear();
+  }
+};
+
+// Runs the chunk loop shared by forward and backward: uploads `ins`, calls `kernels(chunk descriptor, unit range)` on the
+// compute stream, downloads `outs`.  Returns the first library error (FA_OK otherwise); CUDA errors accumulate in C.e.
+template <typename KernelFn>
+static int run_chunks(LegacyCall& C, const fa_attn_desc& a, std::vector<Xfer>& ins, std::vector<Xfer>& outs,
+                      KernelFn&& kernels) {
+  DevPipe& P = *C.P;
+  const int B = a.B, nh = a.H, N = a.N, d = a.d;
+  bool any_staged = false;
+  for (const Xfer& x : ins) any_staged = any_staged || !x.direct;
+  for (const Xfer& x : outs) any_staged = any_staged || !x.direct;
+  std::vector<Chunk> chunks;
+  plan_chunks(B, nh, N, d, any_staged, chunks);
+  const int nc = (int)chunks.size();
+  size_t max_units = 0;
+  for (const Chunk& ck : chunks) max_units = std::max(max_units, (size_t)ck.nb * ck.hc);
+  // ring slot layout: one 256-byte aligned area per staged tensor
+  std::vector<size_t> in_off(ins.size(), 0), out_off(outs.size(), 0);
+  size_t in_slot = 0, out_slot = 0;
+  for (size_t i = 0; i < ins.size(); ++i)
+    if (!ins[i].direct) in_off[i] = in_slot, in_slot += (max_units * ins[i].unit * wire_bytes(ins[i].wire) + 255) & ~(size_t)255;
+  for (size_t i = 0; i < outs.size(); ++i)
+    if (!outs[i].direct)
+      out_off[i] = out_slot, out_slot += (max_units * outs[i].unit * wire_bytes(outs[i].wire) + 255) & ~(size_t)255;
+  if ((in_slot && !P.rin.ensure(in_slot)) || (out_slot && !P.rout.ensure(out_slot)))
+    return set_error(FA_ERR_CUDA, "legacy flash attention: pinned staging allocation failed (%zu + %zu bytes per slot)",
+                     in_slot, out_slot);
+  if (P.events(nc) != FA_OK) return fa_last_status();
+  constexpr int RS = PinnedRing::S;
+  int rc = FA_OK, issued = 0, drained = 0;
+  for (int c = 0; c < nc && rc == FA_OK && C.e == cudaSuccess; ++c) {
+    const Chunk& ck = chunks[c];
+    const size_t u0 = (size_t)ck.b * nh + ck.h0, nu = (size_t)ck.nb * ck.hc;
+    const int s = c % RS;
+    if (in_slot) C.step(P.rin.acquire(s));
+    for (size_t i = 0; i < ins.size(); ++i) C.step(xfer_in(P, ins[i], u0, nu, in_slot ? P.rin.slot(s) + in_off[i] : nullptr));
+    if (in_slot) C.step(P.rin.mark(s, P.in));
+    C.step(cudaEventRecord(P.ev_in[c], P.in));
+    C.step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
+    for (size_t i = 0; i < ins.size() && rc == FA_OK; ++i) rc = xfer_in_cast(ins[i], u0, nu, P.comp);
+    fa_attn_desc ca = a;
+    ca.B = ck.nb, ca.H = ck.hc;
+    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
+    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
+    if (rc == FA_OK) rc = kernels(ca, u0);
+    for (size_t i = 0; i < outs.size() && rc == FA_OK; ++i) rc = xfer_out_cast(outs[i], u0, nu, P.comp);
+    if (rc != FA_OK) break;
+    C.step(cudaEventRecord(P.ev_comp[c], P.comp));
+    C.step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
+    // (slot s of the output ring was drained RS chunks ago -- see below -- so it is free)
+    for (size_t i = 0; i < outs.size(); ++i)
+      C.step(xfer_out(P, outs[i], u0, nu, out_slot ? P.rout.slot(s) + out_off[i] : nullptr, s));
+    if (out_slot) {
+      C.step(P.rout.mark(s, P.out));
+      ++issued;
+      while (issued - drained > RS - 1) C.step(P.rout.drain(drained++ % RS));
+    }
+  }
+  if (out_slot) {
+    while (drained < issued) C.step(P.rout.drain(drained++ % RS));
+    for (int i = 0; i < RS; ++i) P.rout.pending[i].clear(), P.rout.used[i] = false;
+  }
+  // always drain: the caller owns the host buffers and may free them as soon as we return
+  const int saved = (rc != FA_OK) ? fa_last_status() : FA_OK;
+  char saved_msg[512];
+  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
+  saved_msg[sizeof(saved_msg) - 1] = 0;
+  C.step(P.drain());
+  for (int i = 0; i < RS; ++i) P.rin.used[i] = false;
+  if (saved != FA_OK) return set_error(saved, "%s", saved_msg);
+  if (C.e != cudaSuccess) return set_error(FA_ERR_CUDA, "legacy flash attention: %s", cudaGetErrorString(C.e));
+  return FA_OK;
+}
+
+// Fills an Xfer for a caller tensor and, for a DIRECT transfer in bf16 mode, allocates the device fp32 image.
+static bool make_xfer(LegacyCall& C, Xfer& x, float* host, void* dev, size_t unit, size_t units, int wire) {
+  x.host = host, x.dev = static_cast<char*>(dev), x.unit = unit, x.wire = wire;
+  x.direct = use_direct(host, units * unit * 4);
+  x.dev32 = nullptr;
+  if (x.direct && wire == WIRE_BF16) {
+    x.dev32 = static_cast<float*>(C.temp(units * unit * 4));
+    if (!x.dev32) return false;
+  }
+  return true;
+}
+
 // Common driver of the four legacy forward entry points.
 static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, float* m, const float* key_mask,
                            int causal, int B, int nh, int N, int d) {
@@ -393,13 +551,13 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
     set_error(FA_ERR_INVALID, "launch_flashattention_forward: null host pointer");
     return;
   }
-  DevPipe* Pp = current_pipe();
-  if (!Pp) return;
-  DevPipe& P = *Pp;
-  int dev = 0;
-  cudaGetDevice(&dev);
+  LegacyCall C;
+  C.P = current_pipe();
+  if (!C.P) return;
+  DevPipe& P = *C.P;
+  cudaGetDevice(&C.dev);
   const LegacyShape S{B, nh, N, d};
-  const size_t n = S.n(), r = S.r();
+  const size_t n = S.n(), r = S.r(), units = (size_t)B * nh;
   const bool tc = current_mode() == FA_MODE_BF16 && tc_head_dim(d);
   const int wire = tc ? WIRE_BF16 : WIRE_F32;
   const size_t esz = wire_bytes(wire);
@@ -407,122 +565,46 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
 
   // device tensors of this call (kept for the backward when the budget allows)
   FwdEntry E;
-  E.dev = dev, E.wire = wire, E.B = B, E.nh = nh, E.N = N, E.d = d;
+  E.dev = C.dev, E.wire = wire, E.B = B, E.nh = nh, E.N = N, E.d = d;
   E.bytes = 4 * n * esz + 2 * r * 4;
   const size_t sizes[6] = {n * esz, n * esz, n * esz, n * esz, r * 4, r * 4};
   for (int i = 0; i < 6; ++i) {
-    E.dptr[i] = alloc_async(sizes[i], P.in, dev);
+    E.dptr[i] = alloc_async(sizes[i], P.in, C.dev);
     if (!E.dptr[i]) {
       set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed (%zu bytes)", sizes[i]);
       free_entry(E, P.in);
       return;
     }
   }
-  char *dQ_ = static_cast<char*>(E.dptr[0]), *dK_ = static_cast<char*>(E.dptr[1]), *dV_ = static_cast<char*>(E.dptr[2]),
-       *dO_ = static_cast<char*>(E.dptr[3]);
-  float *dm = static_cast<float*>(E.dptr[4]), *dl = static_cast<float*>(E.dptr[5]);
-
-  // bf16 wire: always staged (the narrowing IS the staging copy); fp32 wire: only pageable buffers of some size
-  bool staged = tc || (n * 4 >= ((size_t)256 << 10) && (is_pageable(Q) || is_pageable(K) || is_pageable(V) || is_pageable(O)));
-  std::vector<Chunk> chunks;
-  plan_chunks(B, nh, N, d, staged, chunks);
-  const int nc = (int)chunks.size();
-  size_t max_cn = 0, max_cr = 0;
-  for (const Chunk& ck : chunks) {
-    const size_t cn = (size_t)ck.nb * ck.hc * N * d, cr = (size_t)ck.nb * ck.hc * N;
-    max_cn = cn > max_cn ? cn : max_cn, max_cr = cr > max_cr ? cr : max_cr;
-  }
-  const size_t in_tensor = (max_cn * esz + 255) & ~(size_t)255, stat_tensor = (max_cr * 4 + 255) & ~(size_t)255;
-  if (staged && !(P.rin.ensure(3 * in_tensor) && P.rout.ensure(in_tensor + 2 * stat_tensor))) {
-    if (tc) {
-      set_error(FA_ERR_CUDA, "launch_flashattention_forward: pinned staging allocation failed");
-      free_entry(E, P.in);
-      return;
-    }
-    staged = false;   // fp32 wire can still go straight from the caller's buffers (slow for pageable memory)
-  }
-  if (P.events(nc) != FA_OK) {
+  const size_t ND = (size_t)N * d;
+  std::vector<Xfer> ins(3), outs(3);
+  float* const hin[3] = {Q, K, V};
+  bool ok = true;
+  for (int i = 0; i < 3 && ok; ++i) ok = make_xfer(C, ins[i], hin[i], E.dptr[i], ND, units, wire);
+  ok = ok && make_xfer(C, outs[0], O, E.dptr[3], ND, units, wire) && make_xfer(C, outs[1], m, E.dptr[4], N, units, WIRE_F32) &&
+       make_xfer(C, outs[2], l, E.dptr[5], N, units, WIRE_F32);
+  if (!ok) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed");
+    C.free_temps(P.in);
     free_entry(E, P.in);
     return;
   }
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) {
-    if (e == cudaSuccess) e = x;
-  };
-  constexpr int RS = PinnedRing::S;
-  int rc = FA_OK, issued = 0, drained = 0;
-  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
-    const Chunk& ck = chunks[c];
-    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
-    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
-    const int s = c % RS;
-    if (staged) {
-      step(P.rin.acquire(s));
-      const float* src[3] = {Q + off, K + off, V + off};
-      char* dst[3] = {dQ_ + off * esz, dK_ + off * esz, dV_ + off * esz};
-      for (int t = 0; t < 3; ++t) {
-        char* st = P.rin.slot(s) + t * in_tensor;
-        stage_in(st, src[t], cn, wire);
-        step(cudaMemcpyAsync(dst[t], st, cn * esz, cudaMemcpyHostToDevice, P.in));
-      }
-      step(P.rin.mark(s, P.in));
-    } else {
-      step(cudaMemcpyAsync(dQ_ + off * 4, Q + off, cn * 4, cudaMemcpyHostToDevice, P.in));
-      step(cudaMemcpyAsync(dK_ + off * 4, K + off, cn * 4, cudaMemcpyHostToDevice, P.in));
-      step(cudaMemcpyAsync(dV_ + off * 4, V + off, cn * 4, cudaMemcpyHostToDevice, P.in));
-    }
-    step(cudaEventRecord(P.ev_in[c], P.in));
-    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
-    fa_attn_desc ca = a;
-    ca.B = ck.nb, ca.H = ck.hc;
-    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
-    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
+  char *dQ_ = static_cast<char*>(E.dptr[0]), *dK_ = static_cast<char*>(E.dptr[1]), *dV_ = static_cast<char*>(E.dptr[2]),
+       *dO_ = static_cast<char*>(E.dptr[3]);
+  float *dm = static_cast<float*>(E.dptr[4]), *dl = static_cast<float*>(E.dptr[5]);
+  const int rc = run_chunks(C, a, ins, outs, [&](fa_attn_desc& ca, size_t u0) -> int {
+    const size_t o = u0 * ND * esz, ro = u0 * N;
     if (tc) {
       ca.dtype = FA_DTYPE_BF16;
-      rc = fwd_tc_bf16(&ca, dQ_ + off * 2, dK_ + off * 2, dV_ + off * 2, dO_ + off * 2, dm + roff, dl + roff, P.comp);
-    } else {
-      rc = fa_flash_fwd_dev(&ca, dQ_ + off * 4, dK_ + off * 4, dV_ + off * 4, dO_ + off * 4, dm + roff, dl + roff,
-                            reinterpret_cast<fa_stream_t>(P.comp));
+      return fwd_tc_bf16(&ca, dQ_ + o, dK_ + o, dV_ + o, dO_ + o, dm + ro, dl + ro, P.comp);
     }
-    if (rc != FA_OK) break;
-    step(cudaEventRecord(P.ev_comp[c], P.comp));
-    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
-    if (staged) {
-      // slot s of the output ring was drained RS chunks ago (see the loop below), so it is free
-      char* so = P.rout.slot(s);
-      step(cudaMemcpyAsync(so, dO_ + off * esz, cn * esz, cudaMemcpyDeviceToHost, P.out));
-      step(cudaMemcpyAsync(so + in_tensor, dm + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
-      step(cudaMemcpyAsync(so + in_tensor + stat_tensor, dl + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
-      P.rout.pending[s].push_back({O + off, so, cn, wire});
-      P.rout.pending[s].push_back({m + roff, so + in_tensor, cr, WIRE_F32});
-      P.rout.pending[s].push_back({l + roff, so + in_tensor + stat_tensor, cr, WIRE_F32});
-      step(P.rout.mark(s, P.out));
-      ++issued;
-      while (issued - drained > RS - 1) step(P.rout.drain(drained++ % RS));
-    } else {
-      step(cudaMemcpyAsync(O + off, dO_ + off * 4, cn * 4, cudaMemcpyDeviceToHost, P.out));
-      step(cudaMemcpyAsync(m + roff, dm + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
-      step(cudaMemcpyAsync(l + roff, dl + roff, cr * 4, cudaMemcpyDeviceToHost, P.out));
-    }
-  }
-  if (staged) {
-    while (drained < issued) step(P.rout.drain(drained++ % RS));
-    for (int i = 0; i < RS; ++i) P.rout.pending[i].clear(), P.rout.used[i] = false;
-  }
-  // always drain: the caller owns the host buffers and may free them as soon as we return
-  const int saved = fa_last_status();
-  char saved_msg[512];
-  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
-  saved_msg[sizeof(saved_msg) - 1] = 0;
-  step(P.drain());
-  for (int i = 0; i < RS; ++i) P.rin.used[i] = false;
-  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
-  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_forward: %s", cudaGetErrorString(e));
+    return fa_flash_fwd_dev(&ca, dQ_ + o, dK_ + o, dV_ + o, dO_ + o, dm + ro, dl + ro, reinterpret_cast<fa_stream_t>(P.comp));
+  });
+  C.free_temps(P.comp);
 
   // keep the device tensors for the backward, or let them go
-  const bool ok = fa_last_status() == FA_OK;
   const size_t budget = keep_budget();
-  if (!ok || budget == 0 || E.bytes > budget) {
+  if (rc != FA_OK || budget == 0 || E.bytes > budget) {
     free_entry(E, P.comp);
     return;
   }
@@ -533,7 +615,7 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
   // a new forward over the same buffers replaces the old entry; then evict oldest-first down to the budget
   for (size_t i = 0; i < g_fwd_cache.size();) {
     FwdEntry& o = g_fwd_cache[i];
-    if (o.dev == dev && (o.host[0] == Q || o.host[3] == O)) {
+    if (o.dev == C.dev && (o.host[0] == Q || o.host[3] == O)) {
       free_entry(o, P.comp);
       g_fwd_cache.erase(g_fwd_cache.begin() + i);
     } else {
@@ -547,7 +629,7 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
     for (size_t i = 1; i < g_fwd_cache.size(); ++i)
       if (g_fwd_cache[i].stamp < g_fwd_cache[oldest].stamp) oldest = i;
     total -= g_fwd_cache[oldest].bytes;
-    int cur = dev;
+    const int cur = C.dev;
     if (g_fwd_cache[oldest].dev != cur) cudaSetDevice(g_fwd_cache[oldest].dev);
     free_entry(g_fwd_cache[oldest], nullptr);
     if (g_fwd_cache[oldest].dev != cur) cudaSetDevice(cur);
@@ -586,13 +668,13 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
     set_error(FA_ERR_INVALID, "launch_flashattention_backward: null host pointer");
     return;
   }
-  DevPipe* Pp = current_pipe();
-  if (!Pp) return;
-  DevPipe& P = *Pp;
-  int dev = 0;
-  cudaGetDevice(&dev);
+  LegacyCall C;
+  C.P = current_pipe();
+  if (!C.P) return;
+  DevPipe& P = *C.P;
+  cudaGetDevice(&C.dev);
   const LegacyShape S{B, nh, N, d};
-  const size_t n = S.n(), r = S.r();
+  const size_t n = S.n(), r = S.r(), units = (size_t)B * nh, ND = (size_t)N * d;
   const bool tc = current_mode() == FA_MODE_BF16 && tc_head_dim(d);
   const int wire = tc ? WIRE_BF16 : WIRE_F32;
   const size_t esz = wire_bytes(wire);
@@ -601,12 +683,12 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
   // inputs: Q K V O (wire dtype), m l (fp32) -- from the matching forward if it is still cached -- and dO
   float* const hp[6] = {Q, K, V, O, m, l};
   FwdEntry E;
-  const bool hit = take_cached_forward(dev, wire, S, hp, &E);
+  const bool hit = take_cached_forward(C.dev, wire, S, hp, &E);
   if (!hit) {
     E = FwdEntry();
     const size_t sizes[6] = {n * esz, n * esz, n * esz, n * esz, r * 4, r * 4};
     for (int i = 0; i < 6; ++i) {
-      E.dptr[i] = alloc_async(sizes[i], P.in, dev);
+      E.dptr[i] = alloc_async(sizes[i], P.in, C.dev);
       if (!E.dptr[i]) {
         set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed (%zu bytes)", sizes[i]);
         free_entry(E, P.in);
@@ -615,129 +697,38 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
     }
   }
   void* g[4] = {};   // dO, dQ, dK, dV on the device
-  for (int i = 0; i < 4; ++i) {
-    g[i] = alloc_async(n * esz, P.in, dev);
-    if (!g[i]) {
-      set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed (%zu bytes)", n * esz);
-      for (int k = 0; k < i; ++k) cudaFreeAsync(g[k], P.in);
-      free_entry(E, P.in);
-      return;
-    }
+  bool ok = true;
+  for (int i = 0; i < 4 && ok; ++i) ok = (g[i] = C.temp(n * esz)) != nullptr;
+  std::vector<Xfer> ins, outs(3);
+  if (ok && !hit) {
+    ins.resize(6);
+    for (int i = 0; i < 4 && ok; ++i) ok = make_xfer(C, ins[i], hp[i], E.dptr[i], ND, units, wire);
+    ok = ok && make_xfer(C, ins[4], m, E.dptr[4], N, units, WIRE_F32) && make_xfer(C, ins[5], l, E.dptr[5], N, units, WIRE_F32);
   }
-  auto release_all = [&](cudaStream_t st) {
-    for (void* p : g) cudaFreeAsync(p, st);
-    free_entry(E, st);
-  };
+  if (ok) {
+    ins.emplace_back();
+    ok = make_xfer(C, ins.back(), dO, g[0], ND, units, wire);
+  }
+  float* const hout[3] = {dQ, dK, dV};
+  for (int i = 0; i < 3 && ok; ++i) ok = make_xfer(C, outs[i], hout[i], g[1 + i], ND, units, wire);
+  if (!ok) {
+    set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed");
+    C.free_temps(P.in);
+    free_entry(E, P.in);
+    return;
+  }
   char* din[5] = {static_cast<char*>(E.dptr[0]), static_cast<char*>(E.dptr[1]), static_cast<char*>(E.dptr[2]),
                   static_cast<char*>(E.dptr[3]), static_cast<char*>(g[0])};
   float *dm = static_cast<float*>(E.dptr[4]), *dl = static_cast<float*>(E.dptr[5]);
   char* dout[3] = {static_cast<char*>(g[1]), static_cast<char*>(g[2]), static_cast<char*>(g[3])};
-  float* const host_in[5] = {Q, K, V, O, dO};
-  float* const host_out[3] = {dQ, dK, dV};
-  const int first_in = hit ? 4 : 0;   // a cached forward leaves only dO to upload
-
-  bool staged = tc;
-  if (!staged && n * 4 >= ((size_t)256 << 10)) {
-    bool any = is_pageable(dQ) || is_pageable(dK) || is_pageable(dV);
-    for (int i = first_in; i < 5; ++i) any = any || is_pageable(host_in[i]);
-    staged = any;
-  }
-  std::vector<Chunk> chunks;
-  plan_chunks(B, nh, N, d, staged, chunks);
-  const int nc = (int)chunks.size();
-  size_t max_cn = 0, max_cr = 0;
-  for (const Chunk& ck : chunks) {
-    const size_t cn = (size_t)ck.nb * ck.hc * N * d, cr = (size_t)ck.nb * ck.hc * N;
-    max_cn = cn > max_cn ? cn : max_cn, max_cr = cr > max_cr ? cr : max_cr;
-  }
-  const size_t in_tensor = (max_cn * esz + 255) & ~(size_t)255, stat_tensor = (max_cr * 4 + 255) & ~(size_t)255;
-  const size_t in_slot = (5 - first_in) * in_tensor + (hit ? 0 : 2 * stat_tensor);
-  if (staged && !(P.rin.ensure(in_slot) && P.rout.ensure(3 * in_tensor))) {
-    if (tc) {
-      set_error(FA_ERR_CUDA, "launch_flashattention_backward: pinned staging allocation failed");
-      release_all(P.in);
-      return;
-    }
-    staged = false;
-  }
-  if (P.events(nc) != FA_OK) {
-    release_all(P.in);
-    return;
-  }
-  cudaError_t e = cudaSuccess;
-  auto step = [&](cudaError_t x) {
-    if (e == cudaSuccess) e = x;
-  };
-  constexpr int RS = PinnedRing::S;
-  int rc = FA_OK, issued = 0, drained = 0;
-  for (int c = 0; c < nc && rc == FA_OK && e == cudaSuccess; ++c) {
-    const Chunk& ck = chunks[c];
-    const size_t off = ((size_t)ck.b * nh + ck.h0) * N * d, cn = (size_t)ck.nb * ck.hc * N * d;
-    const size_t roff = ((size_t)ck.b * nh + ck.h0) * N, cr = (size_t)ck.nb * ck.hc * N;
-    const int s = c % RS;
-    if (staged) {
-      step(P.rin.acquire(s));
-      char* st = P.rin.slot(s);
-      for (int i = first_in; i < 5; ++i, st += in_tensor) {
-        stage_in(st, host_in[i] + off, cn, wire);
-        step(cudaMemcpyAsync(din[i] + off * esz, st, cn * esz, cudaMemcpyHostToDevice, P.in));
-      }
-      if (!hit) {
-        stage_in(st, m + roff, cr, WIRE_F32);
-        step(cudaMemcpyAsync(dm + roff, st, cr * 4, cudaMemcpyHostToDevice, P.in));
-        st += stat_tensor;
-        stage_in(st, l + roff, cr, WIRE_F32);
-        step(cudaMemcpyAsync(dl + roff, st, cr * 4, cudaMemcpyHostToDevice, P.in));
-      }
-      step(P.rin.mark(s, P.in));
-    } else {
-      for (int i = first_in; i < 5; ++i)
-        step(cudaMemcpyAsync(din[i] + off * 4, host_in[i] + off, cn * 4, cudaMemcpyHostToDevice, P.in));
-      if (!hit) {
-        step(cudaMemcpyAsync(dm + roff, m + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
-        step(cudaMemcpyAsync(dl + roff, l + roff, cr * 4, cudaMemcpyHostToDevice, P.in));
-      }
-    }
-    step(cudaEventRecord(P.ev_in[c], P.in));
-    step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
-    fa_attn_desc ca = a;
-    ca.B = ck.nb, ca.H = ck.hc;
+  run_chunks(C, a, ins, outs, [&](fa_attn_desc& ca, size_t u0) -> int {
+    const size_t o = u0 * ND * esz, ro = u0 * N;
     ca.dtype = tc ? FA_DTYPE_BF16 : FA_DTYPE_F32;
-    if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
-    if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
-    const size_t o = off * esz;
-    rc = fa_flash_bwd_dev(&ca, din[0] + o, din[1] + o, din[2] + o, din[3] + o, din[4] + o, dm + roff, dl + roff,
-                          dout[0] + o, dout[1] + o, dout[2] + o, reinterpret_cast<fa_stream_t>(P.comp));
-    if (rc != FA_OK) break;
-    step(cudaEventRecord(P.ev_comp[c], P.comp));
-    step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
-    if (staged) {
-      char* so = P.rout.slot(s);
-      for (int i = 0; i < 3; ++i) {
-        step(cudaMemcpyAsync(so + i * in_tensor, dout[i] + o, cn * esz, cudaMemcpyDeviceToHost, P.out));
-        P.rout.pending[s].push_back({host_out[i] + off, so + i * in_tensor, cn, wire});
-      }
-      step(P.rout.mark(s, P.out));
-      ++issued;
-      while (issued - drained > RS - 1) step(P.rout.drain(drained++ % RS));
-    } else {
-      for (int i = 0; i < 3; ++i)
-        step(cudaMemcpyAsync(host_out[i] + off, dout[i] + o, cn * 4, cudaMemcpyDeviceToHost, P.out));
-    }
-  }
-  if (staged) {
-    while (drained < issued) step(P.rout.drain(drained++ % RS));
-    for (int i = 0; i < RS; ++i) P.rout.pending[i].clear(), P.rout.used[i] = false;
-  }
-  const int saved = fa_last_status();
-  char saved_msg[512];
-  strncpy(saved_msg, fa_last_error(), sizeof(saved_msg) - 1);
-  saved_msg[sizeof(saved_msg) - 1] = 0;
-  step(P.drain());
-  for (int i = 0; i < RS; ++i) P.rin.used[i] = false;
-  release_all(P.comp);
-  if (saved != FA_OK) set_error(saved, "%s", saved_msg);
-  else if (e != cudaSuccess) set_error(FA_ERR_CUDA, "launch_flashattention_backward: %s", cudaGetErrorString(e));
+    return fa_flash_bwd_dev(&ca, din[0] + o, din[1] + o, din[2] + o, din[3] + o, din[4] + o, dm + ro, dl + ro, dout[0] + o,
+                            dout[1] + o, dout[2] + o, reinterpret_cast<fa_stream_t>(P.comp));
+  });
+  C.free_temps(P.comp);
+  free_entry(E, P.comp);
 }
 
 }  // namespace fa
