@@ -30,7 +30,7 @@ def test_shard_batch_partitions_exactly():
 def test_aggregator_without_process_group_is_identity():
     agg = Aggregator(None)
     agg.barrier()
-    assert agg.max(3.5) == 3.5 and agg.sum(2.0) == 2.0
+    assert agg.max(3.5) == 3.5 and agg.sum(2.0) == 2.0 and agg.gather(7.0) == [7.0]
     tput, ms = agg.whole_job_throughput(1e12, 10.0)
     assert ms == 10.0 and tput == pytest.approx(1e14)
 
@@ -54,7 +54,7 @@ def _worker(rank, world, port, out):
         local_ms = 100.0 + 25.0 * rank                 # rank 1 is the slow one
         agg.barrier()
         tput, ms = agg.whole_job_throughput(local_flops, local_ms)
-        out.put((rank, b0, b1, tput, ms, agg.max(float(rank)), agg.sum(1.0)))
+        out.put((rank, b0, b1, tput, ms, agg.max(float(rank)), agg.sum(1.0), agg.gather(local_ms)))
     finally:
         dist.destroy_process_group()
 
@@ -71,7 +71,8 @@ def test_two_rank_gloo_aggregation():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, a0, a1, t0, ms0, mx0, sm0), (r1, b0, b1, t1, ms1, mx1, sm1) = res
+    (r0, a0, a1, t0, ms0, mx0, sm0, g0), (r1, b0, b1, t1, ms1, mx1, sm1, g1) = res
+    assert g0 == g1 == [100.0, 125.0]                   # per-rank times in rank order (bench.py `per_rank_ms`)
     assert (a0, a1, b0, b1) == (0, 32, 32, 64)          # disjoint halves of the batch, no overlap
     assert ms0 == ms1 == 125.0                          # max over ranks
     total = 14.0 * 64 * 32 * 8192 * 8192 * 128
