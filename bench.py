@@ -578,16 +578,19 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, steps, dist, path):
     for p in pinned_ptrs:
         lib.fa_free_host(p)
     reuse = (hits.value - hits0.value) > 0
-    # bytes that cross PCIe per step: bf16 on the wire; the backward re-uses the forward's device tensors when cached
-    h2d = 3 * n * 2 + (n * 2 if reuse else (5 * n * 2 + 2 * r * 4)) + (mask.nbytes * 2 if mask is not None else 0)
-    d2h = n * 2 + 2 * r * 4 + 3 * n * 2
+    # bytes that cross PCIe per step: pageable (numpy) tensors are narrowed to bf16 by the staging threads, page-locked
+    # ones go direct as fp32 (cast on the device); the backward re-uses the forward's device tensors when cached.
+    # "ops": inputs are numpy arrays, outputs come from CudaKernelOps' pinned pool; "pinned": everything page-locked.
+    in_b = 2 if path == "ops" else 4
+    h2d = 3 * n * in_b + (n * in_b if reuse else (5 * n * in_b + 2 * r * 4)) + (mask.nbytes * 2 if mask is not None else 0)
+    d2h = n * 4 + 2 * r * 4 + 3 * n * 4
     return {"value": total / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": dt / steps * 1e3, "batch_per_gpu": B,
             "forward_tensors_reused_by_backward": bool(reuse),
             "path": ("CudaKernelOps.flash_attention_fw/_bw(key_mask) on numpy-backed (pageable) fp32 tensors -> legacy C "
-                     "ABI, FA_MODE_BF16, bf16 on the wire" if path == "ops" else
+                     "ABI, FA_MODE_BF16; inputs narrowed to bf16 by the staging threads, results direct into pinned fp32 arrays" if path == "ops" else
                      "launch_flashattention_{forward,backward}_masked by raw ctypes, fp32 page-locked host buffers, "
-                     "FA_MODE_BF16, bf16 on the wire") + "; wall clock incl. H2D/D2H"}
+                     "FA_MODE_BF16; fp32 on the wire (direct DMA), cast on the device") + "; wall clock incl. H2D/D2H"}
 
 
 if __name__ == "__main__":
