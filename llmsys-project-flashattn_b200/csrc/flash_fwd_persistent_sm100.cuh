@@ -47,11 +47,6 @@ __global__ void __launch_bounds__(640, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#ifdef FA_TRACE
-  long long* tr = nullptr;   // (the per-iteration trace of the non-persistent kernel is not wired here)
-  const int j = 0;
-  (void)tr, (void)j;
-#endif
   const int HB = p.H * p.B;
   // work item -> (query block, head, batch) and the number of key tiles each of its two Q tiles sees
   struct Item {

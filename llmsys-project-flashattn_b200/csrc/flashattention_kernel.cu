@@ -236,7 +236,7 @@ static int launch_fwd_tc(const fa_attn_desc* a, const CUtensorMap& tq, const CUt
   return FA_OK;
 }
 
-// OutT = bf16 for the device API; float when the legacy fp32 ABI wants fp32 O straight from the kernel.
+// OutT = bf16 (the only instantiation: the legacy fp32 ABI narrows / widens around the bf16 kernels, legacy_pipeline.cuh).
 template <typename OutT>
 static int fwd_tc(const fa_attn_desc* a, const void* Q, const void* K, const void* V, void* O, long long o_sb,
                   long long o_sh, long long o_sn, float* m, float* l, cudaStream_t st) {
