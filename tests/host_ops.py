@@ -109,3 +109,35 @@ class OracleOps:
         p = np.exp(x - lse.to_numpy().astype(np.float64)[:, None])
         p[np.arange(len(t)), t] -= 1.0
         return _new(logits, out_grad.to_numpy().astype(np.float64)[:, None] * p)
+
+    # decode shapes: numpy KV cache + the decode-attention formula, so that the cache bookkeeping of
+    # MultiHeadAttention.forward_cached / decode_step / generate_cached is testable without a GPU
+    class _Cache:
+        def __init__(self, B, nh, capacity, d):
+            self.B, self.nh, self.capacity, self.d = B, nh, capacity, d
+            self.k = np.zeros((B, nh, capacity, d), dtype=f32)
+            self.v = np.zeros((B, nh, capacity, d), dtype=f32)
+            self.len = 0
+
+    @staticmethod
+    def kv_cache_new(B, nh, capacity, d):
+        return OracleOps._Cache(B, nh, capacity, d)
+
+    @staticmethod
+    def kv_cache_append(cache, k, v):
+        n = k.shape[2]
+        if cache.len + n > cache.capacity:
+            raise ValueError("cache overflow")
+        cache.k[:, :, cache.len:cache.len + n] = k.to_numpy()
+        cache.v[:, :, cache.len:cache.len + n] = v.to_numpy()
+        cache.len += n
+
+    @staticmethod
+    def flash_decode(q, cache):
+        Q = q.to_numpy().astype(np.float64)                       # (B, nh, 1, d)
+        K = cache.k[:, :, :cache.len].astype(np.float64)
+        V = cache.v[:, :, :cache.len].astype(np.float64)
+        s = np.einsum("bhqd,bhkd->bhqk", Q, K) / np.sqrt(Q.shape[-1])
+        p = np.exp(s - s.max(-1, keepdims=True))
+        p /= p.sum(-1, keepdims=True)
+        return _new(q, np.einsum("bhqk,bhkd->bhqd", p, V))

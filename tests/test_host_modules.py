@@ -133,6 +133,32 @@ def test_generate_greedy_matches_stepwise_argmax_and_is_branch_independent():
     assert int(np.argmax(logits[0, -1])) == a[-1]
 
 
+def test_generate_cached_host_logic_matches_full_prefix_loop():
+    """Cache-aware generation (prefill once, then one position per token) through the oracle-backed
+    ops: same greedy tokens as the reference-style full-prefix loop, per-step logits equal the last-position logits of a
+    full forward, cache length bookkeeping, overflow is an error."""
+    z = np.load(golden("decoder_small.npz")[0])
+    model, _ = load_decoder(z, use_flash_attention=True)
+    prompt = [int(t) for t in z["input_ids"][0, :5]]
+    full = fb.generate(model, prompt, model_max_length=12)
+    cached = fb.generate_cached(model, prompt, model_max_length=12)
+    assert cached == full
+    ops = model.backend.ops
+    attn = model.t_layer_1.attention
+    caches = [ops.kv_cache_new(1, attn.n_head, 9, attn.attn_hidden_dim) for _ in range(4)]
+    lg = fb.decode_step(model, np.asarray(full[:6], dtype=np.float32).reshape(1, 6), caches).to_numpy()
+    ref = model(T(np.asarray(full[:6], dtype=np.float32).reshape(1, 6))).to_numpy()
+    np.testing.assert_allclose(lg, ref, atol=2e-5, rtol=1e-5)
+    for t in range(6, 9):
+        lg = fb.decode_step(model, np.asarray([[full[t]]], dtype=np.float32), caches).to_numpy()
+        ref = model(T(np.asarray(full[:t + 1], dtype=np.float32).reshape(1, t + 1))).to_numpy()
+        np.testing.assert_allclose(lg[0, 0], ref[0, t], atol=2e-5, rtol=1e-5)
+    assert [c.len for c in caches] == [9] * 4
+    import pytest
+    with pytest.raises(ValueError):
+        fb.decode_step(model, np.asarray([[full[9]]], dtype=np.float32), caches)
+
+
 def test_module_tree_train_eval_and_dropout():
     """Module.train()/eval() reach every sub-module; Dropout is the identity at p = 0 or in eval mode and rescales
     by 1/(1-p) in training (minitorch/modules_basic.py:73-101)."""
