@@ -6,9 +6,12 @@
 // into flashattention_kernel.so (compile_cuda.sh); bit-identical to cvt.rn.bf16.f32 (round to nearest even, NaN stays NaN).
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <immintrin.h>
 
 namespace {
+
+bool stream_stores();
 
 inline uint16_t narrow_one(uint32_t u) {
   if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);
@@ -31,28 +34,50 @@ __attribute__((target("avx2"))) inline __m256i narrow8(__m256i u) {
   return _mm256_blendv_epi8(rounded, quiet, is_nan);   // 8 x (0x0000hhhh)
 }
 
+// The destinations of both conversions are written once and not read again by this core (the staging slot is read by
+// the DMA engine, the caller's result array by the caller much later), so 32-byte aligned destinations get streaming
+// stores: no read-for-ownership of the destination lines, a third less memory traffic for the narrowing pass.
 __attribute__((target("avx2"))) void narrow_avx2(uint16_t* dst, const uint32_t* src, size_t n) {
   size_t i = 0;
+  const bool stream = stream_stores() && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
   for (; i + 16 <= n; i += 16) {
     const __m256i a = narrow8(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)));
     const __m256i b = narrow8(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 8)));
     // packus works per 128-bit lane: [a0-3 b0-3 | a4-7 b4-7] -> permute the 64-bit quarters back into order
     const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8);
-    _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), p);
+    if (stream) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), p);
+    else _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), p);
   }
+  if (stream) _mm_sfence();   // streaming stores are ordered before whatever publishes the buffer (the DMA doorbell)
   narrow_scalar(dst + i, src + i, n - i);
 }
 
 __attribute__((target("avx2"))) void widen_avx2(uint32_t* dst, const uint16_t* src, size_t n) {
   size_t i = 0;
+  const bool stream = stream_stores() && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
   for (; i + 16 <= n; i += 16) {
     const __m256i h = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
     const __m256i lo = _mm256_slli_epi32(_mm256_cvtepu16_epi32(_mm256_castsi256_si128(h)), 16);
     const __m256i hi = _mm256_slli_epi32(_mm256_cvtepu16_epi32(_mm256_extracti128_si256(h, 1)), 16);
-    _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), lo);
-    _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i + 8), hi);
+    if (stream) {
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), lo);
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 8), hi);
+    } else {
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), lo);
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i + 8), hi);
+    }
   }
+  if (stream) _mm_sfence();
   widen_scalar(dst + i, src + i, n - i);
+}
+
+// streaming (non-temporal) stores for 32-byte aligned destinations: env MINITORCH_FA_STREAM_STORES=0 turns them off
+bool stream_stores() {
+  static const bool v = [] {
+    const char* e = getenv("MINITORCH_FA_STREAM_STORES");
+    return !(e && e[0] == '0');
+  }();
+  return v;
 }
 
 bool have_avx2() {
