@@ -62,11 +62,21 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (p.K + BK - 1) / BK;
-  // PERSISTENT: a CTA walks output tiles t = blockIdx.x, + gridDim.x, ...; tiles are numbered with the N index fastest,
-  // so the CTAs that run together share rows of A and all of B (weights) through L2.  Two accumulator stages in TMEM
-  // let the epilogue of tile i (TMEM -> registers -> global) run under the MMAs of tile i+1.
+  // PERSISTENT: a CTA walks output tiles t = blockIdx.x, + gridDim.x, ... (grouped order, see tile_origin).  Two
+  // accumulator stages in TMEM let the epilogue of tile i (TMEM -> registers -> global) run under the MMAs of tile i+1.
   const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
   const int n_tiles = tiles_n * tiles_m;
+  // tile t -> (m0, n0): bands of GROUP_M row panels, M index fastest inside a band, so the ~148 tiles in flight cover GROUP_M row panels x ~148/GROUP_M column panels -- a squarer footprint than one
+  // row of tiles (8192^3: B was re-streamed from HBM once per 4.6 row panels, 2.0 GB of DRAM reads per launch)
+  constexpr int GROUP_M = 8;
+  auto tile_origin = [&](int t, int& m0, int& n0) {
+    const int band = t / (GROUP_M * tiles_n);
+    const int first_m = band * GROUP_M;
+    const int rows = min(GROUP_M, tiles_m - first_m);
+    const int r = t - band * GROUP_M * tiles_n;
+    m0 = (first_m + r % rows) * BM;
+    n0 = (r / rows) * BN;
+  };
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -92,7 +102,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (lane == 0) {
       uint32_t it = 0;     // stage counter across tiles
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int n0 = (t % tiles_n) * BN, m0 = (t / tiles_n) * BM;
+        int m0, n0;
+        tile_origin(t, m0, n0);
         for (int kt = 0; kt < nk; ++kt, ++it) {
           const int s = it % NSTAGE;
           mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
@@ -154,7 +165,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
     uint32_t tc = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tc) {
-      const int n0 = (t % tiles_n) * BN, m0 = (t / tiles_n) * BM;
+      int m0, n0;
+      tile_origin(t, m0, n0);
       const uint32_t as = tc % ACC_STAGES;
       mbar_wait(&acc_full[as], (tc / ACC_STAGES) & 1);
       tc_fence_after();
