@@ -28,7 +28,8 @@ template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;   // per epilogue warp a [32 rows][36] fp32 transpose tile
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct Params {
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   constexpr int ACC_STAGES = 512 / BN >= 2 ? 2 : 1;      // accumulator stages in TMEM (2 x 256 or 2 x 128 columns)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  float* epi = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES + Cfg<BN>::EPI_BYTES);
   uint64_t* full = bars;                 // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t* acc_full = bars + 2 * NSTAGE;      // [2]  accumulator stage complete (MMA -> epilogue)
@@ -182,39 +184,49 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           mbar_arrive(&acc_empty[as]);
         }
         const int col0 = n0 + 32 * c;
-        if (row < p.M && col0 < p.N) {
-          // destination: column block j of width n_split lives in out[j]
-          int j = 0, cj = col0;
-          if (p.n_split > 0) {
-            j = col0 / p.n_split;
-            cj = col0 - j * p.n_split;
+        // destination: column block j of width n_split lives in out[j]
+        int j = 0, cj = col0;
+        if (p.n_split > 0) {
+          j = col0 / p.n_split;
+          cj = col0 - j * p.n_split;
+        }
+        const int valid = min(32, p.N - col0);      // (<= 0 when the piece is past the last column)
+        if ((p.ldo & 3) == 0 && (cj & 3) == 0 && (valid & 3) == 0) {
+          // Coalesced path: the accumulator arrives with lane = row; a per-warp shared-memory transpose turns it into
+          // lane = 4 consecutive columns, so one store instruction writes 4 rows x 128 contiguous bytes instead of 32
+          // scattered 16-byte pieces (the output of a short-K GEMM is a gigabyte: 131072 x 2048 fp32).
+          float* T = epi + warp * (32 * 36);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(T + lane * 36 + 4 * k) =
+                make_float4(__uint_as_float(u[4 * k]), __uint_as_float(u[4 * k + 1]), __uint_as_float(u[4 * k + 2]),
+                            __uint_as_float(u[4 * k + 3]));
+          __syncwarp();
+          const int cq = (lane & 7) * 4;      // my 4 columns of the piece
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int r = rr + (lane >> 3);
+            const float4 v = *reinterpret_cast<const float4*>(T + r * 36 + cq);
+            const int grow = m0 + warp * 32 + r;
+            if (grow < p.M && cq < valid) {
+              if (p.out_bf16) {
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out[j]) + static_cast<long long>(grow) * p.ldo + cj + cq;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+              } else {
+                float* dst = static_cast<float*>(p.out[j]) + static_cast<long long>(grow) * p.ldo + cj + cq;
+                *reinterpret_cast<float4*>(dst) = v;
+              }
+            }
           }
-          const int valid = min(32, p.N - col0);
+          __syncwarp();      // the tile is reused by the next piece
+        } else if (row < p.M && valid > 0) {
+          // ragged / unaligned outputs: element-wise stores, lane = row
           if (p.out_bf16) {
             __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out[j]) + static_cast<long long>(row) * p.ldo + cj;
-            if (valid == 32 && (p.ldo & 7) == 0 && (cj & 7) == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 o;
-                o.x = pack_bf16x2(__uint_as_float(u[8 * i]), __uint_as_float(u[8 * i + 1]));
-                o.y = pack_bf16x2(__uint_as_float(u[8 * i + 2]), __uint_as_float(u[8 * i + 3]));
-                o.z = pack_bf16x2(__uint_as_float(u[8 * i + 4]), __uint_as_float(u[8 * i + 5]));
-                o.w = pack_bf16x2(__uint_as_float(u[8 * i + 6]), __uint_as_float(u[8 * i + 7]));
-                reinterpret_cast<uint4*>(dst)[i] = o;
-              }
-            } else {
-              for (int i = 0; i < valid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(u[i]));
-            }
+            for (int i = 0; i < valid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(u[i]));
           } else {
             float* dst = static_cast<float*>(p.out[j]) + static_cast<long long>(row) * p.ldo + cj;
-            if (valid == 32 && (p.ldo & 3) == 0 && (cj & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
-                                                                __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3]));
-            } else {
-              for (int i = 0; i < valid; ++i) dst[i] = __uint_as_float(u[i]);
-            }
+            for (int i = 0; i < valid; ++i) dst[i] = __uint_as_float(u[i]);
           }
         }
       }
