@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 namespace fa {
 namespace decode {
 
@@ -33,16 +35,17 @@ struct Vec;
 template <>
 struct Vec<float> {
   static constexpr int N = 4;
-  __device__ static void load(const float* p, float (&v)[4]) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
-  }
+  using Raw = float4;
+  __device__ static Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static void unpack(const Raw& x, float (&v)[4]) { v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w; }
+  __device__ static void load(const float* p, float (&v)[4]) { unpack(load_raw(p), v); }
 };
 template <>
 struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
-  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+  using Raw = uint4;
+  __device__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static void unpack(const Raw& x, float (&v)[8]) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -50,6 +53,7 @@ struct Vec<__nv_bfloat16> {
       v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
   }
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) { unpack(load_raw(p), v); }
 };
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -93,32 +97,42 @@ __global__ void __launch_bounds__(kWarps * 32)
   const T* kb = kc + b * p.c_sb + h * p.c_sh;
   const T* vb = vc + b * p.c_sb + h * p.c_sh;
   // UNR keys per lane group and step: their K and V vectors are all requested before any arithmetic, so a lane keeps
-  // 2 * UNR * NV 16-byte loads in flight (with one key per step the kernel ran at 0.55 of the HBM peak: latency-bound)
+  // 2 * UNR * NV 16-byte loads in flight (with one key per step the kernel ran at 0.55 of the HBM peak: latency-bound).
+  // The vectors stay RAW (16 bytes = 4 registers, whatever T is) until they are consumed: unpacking bf16 to floats
+  // right after the load cost 115 registers and 4 CTAs per SM, and bf16 caches ran at 0.51 of the HBM peak; raw, the
+  // kernel needs 80 (6 CTAs per SM) and reaches it.  (A software-pipelined loop over two register sets was tried on
+  // top: 121 registers, 0.65 -- occupancy is worth more here than a warp that never idles.)
   constexpr int UNR = (NV == 1) ? 4 : 2;
-  for (int n0 = k_begin + warp * KPW * UNR; n0 < k_end; n0 += kWarps * KPW * UNR) {
-    float kv_[UNR][NV][VN], vv_[UNR][NV][VN];
-    bool ok[UNR];
+  using Raw = typename Vec<T>::Raw;
+  const int stride = kWarps * KPW * UNR;
+  auto issue = [&](int n0, Raw (&kr)[UNR][NV], Raw (&vr)[UNR][NV]) {
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int n = n0 + u * KPW + grp;
-      ok[u] = n < k_end;
-      const long long roff = static_cast<long long>(ok[u] ? n : k_begin) * p.c_sn;   // (clamped: the load stays in bounds)
+      const long long roff = static_cast<long long>(n < k_end ? n : k_begin) * p.c_sn;   // (clamped: stays in bounds)
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (live[i]) {
-          Vec<T>::load(kb + roff + (sub + i * LPK) * VN, kv_[u][i]);
-          Vec<T>::load(vb + roff + (sub + i * LPK) * VN, vv_[u][i]);
+          kr[u][i] = Vec<T>::load_raw(kb + roff + (sub + i * LPK) * VN);
+          vr[u][i] = Vec<T>::load_raw(vb + roff + (sub + i * LPK) * VN);
         }
     }
+  };
+  auto consume = [&](int n0, const Raw (&kr)[UNR][NV], const Raw (&vr)[UNR][NV]) {
     float s[UNR];
+    bool ok[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
+      ok[u] = n0 + u * KPW + grp < k_end;
       s[u] = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (live[i])
+        if (live[i]) {
+          float kf[VN];
+          Vec<T>::unpack(kr[u][i], kf);
 #pragma unroll
-          for (int x = 0; x < VN; ++x) s[u] = fmaf(qv[i][x], kv_[u][i][x], s[u]);
+          for (int x = 0; x < VN; ++x) s[u] = fmaf(qv[i][x], kf[x], s[u]);
+        }
     }
 #pragma unroll
     for (int off = LPK / 2; off > 0; off >>= 1)
@@ -144,14 +158,24 @@ __global__ void __launch_bounds__(kWarps * 32)
       l = l * corr + psum;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (live[i])
+        if (live[i]) {
 #pragma unroll
-          for (int x = 0; x < VN; ++x) {
-            float acc = o[i][x] * corr;
+          for (int x = 0; x < VN; ++x) o[i][x] *= corr;
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) acc = fmaf(pr[u], vv_[u][i][x], acc);
-            o[i][x] = acc;
+          for (int u = 0; u < UNR; ++u) {
+            float vf[VN];
+            Vec<T>::unpack(vr[u][i], vf);
+#pragma unroll
+            for (int x = 0; x < VN; ++x) o[i][x] = fmaf(pr[u], vf[x], o[i][x]);
           }
+        }
+    }
+  };
+  {
+    Raw kr[UNR][NV], vr[UNR][NV];
+    for (int n0 = k_begin + warp * KPW * UNR; n0 < k_end; n0 += stride) {
+      issue(n0, kr, vr);
+      consume(n0, kr, vr);
     }
   }
   // merge the lane groups of this warp (lanes with equal `sub` hold the same slice of d)

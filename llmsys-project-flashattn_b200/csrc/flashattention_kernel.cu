@@ -544,10 +544,17 @@ int fa_flash_decode_dev(const fa_decode_desc* a, const void* q, const void* k_ca
                      "<= %d", a->d, VN, 64 * VN);
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->d);
   p.lse = lse;
-  // split the cache so that about two waves of CTAs cover the 148 SMs, at least 256 keys per split
+  // Split the cache so that the CTAs fill ONE co-resident wave and no more (a second, partial wave costs a whole
+  // tail): 148 SMs x the CTAs of 4 warps that fit one (80 registers with bf16 caches -> 6, 64 with fp32 -> 8), at
+  // least 128 keys per split.  MINITORCH_FA_DECODE_SPLITS forces a count (experiments).
+  static const int forced = [] {
+    const char* e = getenv("MINITORCH_FA_DECODE_SPLITS");
+    return e ? atoi(e) : 0;
+  }();
   const int Lmax = a->kv_len ? cap : a->L;
-  int nsplit = (2 * 148 + a->B * a->H - 1) / (a->B * a->H);
-  const int max_split = (Lmax + 255) / 256;
+  const int slots = 148 * (a->dtype == FA_DTYPE_BF16 ? 6 : 8);
+  int nsplit = forced > 0 ? forced : (int)(slots / ((long long)a->B * a->H));
+  const int max_split = (Lmax + 127) / 128;
   nsplit = nsplit > max_split ? max_split : nsplit;
   nsplit = nsplit < 1 ? 1 : (nsplit > 64 ? 64 : nsplit);
   p.nsplit = nsplit;

@@ -69,7 +69,10 @@ def test_decode_kernel_vs_oracle(dtype, B, H, d, cap, lens):
         a.L = lens[0]
         out2 = dev.DeviceArray((B, H, d), dtype)
         _lib.check(lib, lib.fa_flash_decode_dev(ctypes.byref(a), dq.ptr, dK.ptr, dV.ptr, out2.ptr, None, None))
-        np.testing.assert_array_equal(out2.to_numpy(), out.to_numpy())
+        if cap == lens[0]:       # same split of the cache in both calls: bit-identical
+            np.testing.assert_array_equal(out2.to_numpy(), out.to_numpy())
+        else:                    # the split follows the capacity when only kv_len[] is known: same result up to rounding
+            assert np.abs(out2.to_numpy() - out.to_numpy()).max() < tol / 4
 
 
 def test_decode_rejects_unsupported_head_dim():
