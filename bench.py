@@ -563,11 +563,15 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, steps, dist, path):
     step()
     barrier(dist)
     lib.fa_sync()
+    w0 = (ctypes.c_ulonglong(0), ctypes.c_ulonglong(0))
+    lib.fa_wire_bytes(ctypes.byref(w0[0]), ctypes.byref(w0[1]))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     lib.fa_sync()
     local_dt = time.perf_counter() - t0
+    w1 = (ctypes.c_ulonglong(0), ctypes.c_ulonglong(0))
+    lib.fa_wire_bytes(ctypes.byref(w1[0]), ctypes.byref(w1[1]))
     barrier(dist)
     dt = reduce_max(dist, local_dt)
     total = reduce_sum(dist, flops_step * steps)
@@ -578,19 +582,21 @@ def run_e2e(fb, lib, B, H, N, d, causal, kv_len, steps, dist, path):
     for p in pinned_ptrs:
         lib.fa_free_host(p)
     reuse = (hits.value - hits0.value) > 0
-    # bytes that cross PCIe per step: pageable (numpy) tensors are narrowed to bf16 by the staging threads, page-locked
-    # ones go direct as fp32 (cast on the device); the backward re-uses the forward's device tensors when cached.
-    # "ops": inputs are numpy arrays, outputs come from CudaKernelOps' pinned pool; "pinned": everything page-locked.
-    in_b = 2 if path == "ops" else 4
-    h2d = 3 * n * in_b + (n * in_b if reuse else (5 * n * in_b + 2 * r * 4)) + (mask.nbytes * 2 if mask is not None else 0)
-    d2h = n * 4 + 2 * r * 4 + 3 * n * 4
+    # bytes that crossed PCIe per step, counted by the library where it hands them to the DMA engine (fa_wire_bytes):
+    # pageable (numpy) tensors are narrowed to bf16 by the staging threads; page-locked ones are split between that
+    # route and fp32 by direct DMA + a cast on the device, so that the link and the host cores finish together; the
+    # backward re-uses the forward's device tensors when cached.
+    h2d = (w1[0].value - w0[0].value) // steps
+    d2h = (w1[1].value - w0[1].value) // steps
     return {"value": total / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": dt / steps * 1e3, "batch_per_gpu": B,
             "forward_tensors_reused_by_backward": bool(reuse),
             "path": ("CudaKernelOps.flash_attention_fw/_bw(key_mask) on numpy-backed (pageable) fp32 tensors -> legacy C "
-                     "ABI, FA_MODE_BF16; inputs narrowed to bf16 by the staging threads, results direct into pinned fp32 arrays" if path == "ops" else
+                     "ABI, FA_MODE_BF16; inputs narrowed to bf16 by the staging threads, results into pinned fp32 arrays partly by direct "
+                     "DMA, partly as bf16 widened by the staging threads" if path == "ops" else
                      "launch_flashattention_{forward,backward}_masked by raw ctypes, fp32 page-locked host buffers, "
-                     "FA_MODE_BF16; fp32 on the wire (direct DMA), cast on the device") + "; wall clock incl. H2D/D2H"}
+                     "FA_MODE_BF16; each tensor split between fp32 by direct DMA (cast on the device) and bf16 through the "
+                     "staging threads") + "; wall clock incl. H2D/D2H"}
 
 
 if __name__ == "__main__":

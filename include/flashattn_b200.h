@@ -87,6 +87,15 @@ void fa_set_keep_forward_mb(long long mb);
 void fa_forward_cache_stats(unsigned long long* hits, unsigned long long* misses);
 /* Times a pinned staging ring could not be allocated and a call fell back to direct (slow, pageable) copies. */
 unsigned long long fa_staging_fallbacks(void);
+/* Bytes the legacy entry points have handed to the DMA engine since the library was loaded, per direction.  In bf16 mode
+ * a page-locked caller tensor is split between two routes -- fp32 image by DMA + cast on the device, or narrowed /
+ * widened by the host threads with bf16 on the wire -- in the proportion that lets the link and the host cores finish
+ * together (env MINITORCH_FA_HYBRID=0 disables the split, MINITORCH_FA_HYBRID_COST sets the host/DMA cost ratio). */
+void fa_wire_bytes(unsigned long long* h2d, unsigned long long* d2h);
+/* The split above, set explicitly: host_cost = time of the host route for one tensor relative to its direct DMA as fp32
+ * (> 0: used as given; 0: MINITORCH_FA_HYBRID_COST or the built-in 0.8 scaled by 16 / staging threads; < 0: no split,
+ * page-locked tensors always go direct).  Tensors smaller than min_tensor_bytes (< 0: the default 32 MiB) are never split. */
+void fa_set_transfer_policy(double host_cost, long long min_tensor_bytes);
 /* Release the pinned staging rings and the cached forward tensors of the current device. */
 int fa_release_staging(void);
 

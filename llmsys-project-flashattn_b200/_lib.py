@@ -83,6 +83,8 @@ SYMBOLS = {
         "fa_set_keep_forward_mb": (None, [c_longlong]),
         "fa_forward_cache_stats": (None, [POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),
         "fa_staging_fallbacks": (ctypes.c_ulonglong, []),
+        "fa_set_transfer_policy": (None, [ctypes.c_double, c_longlong]),
+        "fa_wire_bytes": (None, [POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),
         "fa_release_staging": (c_int, []),
         "launch_flashattention_forward": (None, _HOST4),
         "launch_flashattention_forward_causal": (None, _HOST4),

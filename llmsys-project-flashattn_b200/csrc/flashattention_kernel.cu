@@ -602,6 +602,14 @@ void fa_forward_cache_stats(unsigned long long* hits, unsigned long long* misses
   if (misses) *misses = g_fwd_misses;
 }
 unsigned long long fa_staging_fallbacks(void) { return g_staging_fallbacks; }
+void fa_set_transfer_policy(double host_cost, long long min_tensor_bytes) {
+  g_hybrid_cost = host_cost;
+  g_hybrid_min_bytes = min_tensor_bytes < 0 ? ((size_t)32 << 20) : (size_t)min_tensor_bytes;
+}
+void fa_wire_bytes(unsigned long long* h2d, unsigned long long* d2h) {
+  if (h2d) *h2d = g_wire_h2d.load();
+  if (d2h) *d2h = g_wire_d2h.load();
+}
 // Gives back what the legacy entry points hold between calls on the current device: the pinned staging rings and the
 // device copies of forward calls that are still waiting for their backward.
 int fa_release_staging(void) {

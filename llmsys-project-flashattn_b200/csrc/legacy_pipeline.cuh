@@ -9,6 +9,8 @@
 //     which halves the bytes on the link in both directions;
 //   * the device copies of Q, K, V, O, m, l made by a forward call stay alive (bounded LRU, validated by host pointer,
 //     shape and a sampled fingerprint of the contents) so the matching backward call uploads only dO;
+//   * page-locked caller tensors are split between the two routes (DMA of the fp32 image + cast on the device / host
+//     threads + bf16 on the wire) so that the link and the host cores finish together (plan_hybrid);
 //   * all per-device state (streams, events, pinned rings) is indexed by device, created once and reused.
 // Included by flashattention_kernel.cu only.
 #pragma once
@@ -150,6 +152,7 @@ static bool is_pageable(const void* p) {
 
 // ------------------------------------------------------------------------------------------------ per-device state
 static unsigned long long g_staging_fallbacks = 0;   // pinned ring could not be allocated -> direct (slow) copies
+static std::atomic<unsigned long long> g_wire_h2d{0}, g_wire_d2h{0};   // bytes handed to the DMA engine (fa_wire_bytes)
 
 struct PinnedRing {
   static constexpr int S = 3;          // chunks in flight
@@ -261,14 +264,15 @@ static bool g_chunk_explicit = false;
 // About chunk_bytes of fp32 per tensor and chunk: whole batches when a batch fits (small problems become ONE chunk:
 // every extra chunk costs ~10 driver calls), otherwise groups of heads inside one batch.  A chunk never straddles a
 // batch boundary unless it holds whole batches, so kv_len / the key mask index by the chunk's first batch.
-static void plan_chunks(int B, int nh, int N, int d, bool staged, std::vector<Chunk>& out) {
+static void plan_chunks(int B, int nh, int N, int d, int staged_kind, std::vector<Chunk>& out) {
   if (!g_chunk_bytes) {
     const char* e = getenv("MINITORCH_FA_CHUNK_MB");
     const long mb = e ? atol(e) : 16;
     g_chunk_explicit = e != nullptr;
     g_chunk_bytes = (size_t)(mb > 0 ? mb : 16) << 20;
   }
-  const size_t chunk_bytes = (staged && !g_chunk_explicit) ? ((size_t)64 << 20) : g_chunk_bytes;
+  const size_t chunk_bytes =
+      (staged_kind && !g_chunk_explicit) ? ((size_t)(staged_kind == 2 ? 64 : 32) << 20) : g_chunk_bytes;
   const size_t head_bytes = (size_t)N * d * 4;
   const size_t batch_bytes = head_bytes * nh;
   out.clear();
@@ -309,10 +313,12 @@ static int stage_mask(fa_attn_desc* a, const float* key_mask, int slot) {
   std::vector<int> h_kv(a->B);
   if (mask_to_kv_len(key_mask, a->B, a->N, h_kv.data())) {
     FA_CUDA_CHECK(cudaMemcpy(d, h_kv.data(), (size_t)a->B * 4, cudaMemcpyHostToDevice));
+    g_wire_h2d += (size_t)a->B * 4;
     a->kv_len = reinterpret_cast<const int*>(d);
   } else {
     char* dm = d + (((size_t)a->B * 4 + 15) & ~size_t(15));
     FA_CUDA_CHECK(cudaMemcpy(dm, key_mask, (size_t)a->B * a->N * 4, cudaMemcpyHostToDevice));
+    g_wire_h2d += (size_t)a->B * a->N * 4;
     a->key_mask = reinterpret_cast<const float*>(dm);
   }
   return FA_OK;
@@ -390,45 +396,57 @@ static int fwd_tc_bf16(const fa_attn_desc* a, const void* Q, const void* K, cons
 //     (bf16 mode) while they copy: a pageable buffer has to be touched by the CPU once anyway, and bf16 halves what the
 //     DMA engine then moves.
 // Tiny tensors always go direct (pageable cudaMemcpyAsync is fine below a few hundred KiB).
+// HYBRID (page-locked tensors in bf16 mode): the link and the host cores are independent resources, so a call whose
+// critical direction is all-DIRECT leaves the cores idle and one that is all-STAGED leaves half the link idle.
+// plan_hybrid() below moves quarter-tensors from the DMA engine to the staging threads until the two finish together;
+// a tensor then takes the staged route on `staged_q` chunks of every 4 and the direct route on the others.
 struct Xfer {
   float* host = nullptr;      // caller buffer (fp32)
   char* dev = nullptr;        // device tensor in the kernels' dtype (wire dtype: bf16 or fp32)
   float* dev32 = nullptr;     // device fp32 image for DIRECT transfers in bf16 mode (nullptr otherwise)
-  bool direct = true;
+  bool direct = true;         // page-locked (or tiny): the DMA engine can reach the caller's buffer
+  int staged_q = 0;           // chunks of every 4 that go through the staging threads: 0 = all direct, 4 = all staged
   size_t unit = 0;            // elements per (batch, head) unit: N*d, or N for the statistics
   int wire = WIRE_F32;        // dtype of `dev`
+  bool staged_at(int c) const { return ((c + 1) * staged_q) / 4 != (c * staged_q) / 4; }
+  bool ever_staged() const { return staged_q > 0; }
+  bool ever_direct() const { return staged_q < 4; }
 };
 static bool use_direct(const void* host, size_t total_bytes) { return total_bytes < ((size_t)256 << 10) || !is_pageable(host); }
 
 // host -> device for the units [u0, u0 + nu) of tensor x (async on P.in; `stage` = this tensor's area of the ring slot)
-static cudaError_t xfer_in(DevPipe& P, const Xfer& x, size_t u0, size_t nu, char* stage) {
+static cudaError_t xfer_in(DevPipe& P, const Xfer& x, int c, size_t u0, size_t nu, char* stage) {
   const size_t off = u0 * x.unit, cnt = nu * x.unit;
-  if (x.direct) {
+  if (!x.staged_at(c)) {
     void* dst = x.dev32 ? static_cast<void*>(x.dev32 + off) : static_cast<void*>(x.dev + off * 4);
+    g_wire_h2d += cnt * 4;
     return cudaMemcpyAsync(dst, x.host + off, cnt * 4, cudaMemcpyHostToDevice, P.in);
   }
   stage_in(stage, x.host + off, cnt, x.wire);
+  g_wire_h2d += cnt * wire_bytes(x.wire);
   return cudaMemcpyAsync(x.dev + off * wire_bytes(x.wire), stage, cnt * wire_bytes(x.wire), cudaMemcpyHostToDevice, P.in);
 }
 // device-side narrowing of a DIRECT fp32 upload (compute stream, before the kernels of the chunk)
-static int xfer_in_cast(const Xfer& x, size_t u0, size_t nu, cudaStream_t comp) {
-  if (!x.dev32) return FA_OK;
+static int xfer_in_cast(const Xfer& x, int c, size_t u0, size_t nu, cudaStream_t comp) {
+  if (!x.dev32 || x.staged_at(c)) return FA_OK;
   const size_t off = u0 * x.unit, cnt = nu * x.unit;
   return fa_cast_f32_to_bf16_dev(x.dev32 + off, x.dev + off * 2, cnt, reinterpret_cast<fa_stream_t>(comp));
 }
 // device-side widening of a result that will be downloaded DIRECTLY (compute stream, after the kernels of the chunk)
-static int xfer_out_cast(const Xfer& x, size_t u0, size_t nu, cudaStream_t comp) {
-  if (!x.dev32) return FA_OK;
+static int xfer_out_cast(const Xfer& x, int c, size_t u0, size_t nu, cudaStream_t comp) {
+  if (!x.dev32 || x.staged_at(c)) return FA_OK;
   const size_t off = u0 * x.unit, cnt = nu * x.unit;
   return fa_cast_bf16_to_f32_dev(x.dev + off * 2, x.dev32 + off, cnt, reinterpret_cast<fa_stream_t>(comp));
 }
 // device -> host (async on P.out); a staged tensor lands in the ring slot and is handed to the caller by drain()
-static cudaError_t xfer_out(DevPipe& P, const Xfer& x, size_t u0, size_t nu, char* stage, int slot) {
+static cudaError_t xfer_out(DevPipe& P, const Xfer& x, int c, size_t u0, size_t nu, char* stage, int slot) {
   const size_t off = u0 * x.unit, cnt = nu * x.unit;
-  if (x.direct) {
+  if (!x.staged_at(c)) {
     const void* src = x.dev32 ? static_cast<const void*>(x.dev32 + off) : static_cast<const void*>(x.dev + off * 4);
+    g_wire_d2h += cnt * 4;
     return cudaMemcpyAsync(x.host + off, src, cnt * 4, cudaMemcpyDeviceToHost, P.out);
   }
+  g_wire_d2h += cnt * wire_bytes(x.wire);
   const cudaError_t e = cudaMemcpyAsync(stage, x.dev + off * wire_bytes(x.wire), cnt * wire_bytes(x.wire),
                                         cudaMemcpyDeviceToHost, P.out);
   P.rout.pending[slot].push_back({x.host + off, stage, cnt, x.wire});
@@ -461,11 +479,13 @@ static int run_chunks(LegacyCall& C, const fa_attn_desc& a, std::vector<Xfer>& i
                       KernelFn&& kernels) {
   DevPipe& P = *C.P;
   const int B = a.B, nh = a.H, N = a.N, d = a.d;
-  bool any_staged = false;
-  for (const Xfer& x : ins) any_staged = any_staged || !x.direct;
-  for (const Xfer& x : outs) any_staged = any_staged || !x.direct;
+  // chunk size: 64 MiB per tensor when a tensor is staged throughout (pageable callers), 32 MiB when tensors alternate
+  // between the routes (the pattern needs a dozen chunks to average out), the direct default otherwise
+  int staged_kind = 0;
+  for (const Xfer& x : ins) staged_kind = std::max(staged_kind, x.staged_q == 4 ? 2 : (x.staged_q ? 1 : 0));
+  for (const Xfer& x : outs) staged_kind = std::max(staged_kind, x.staged_q == 4 ? 2 : (x.staged_q ? 1 : 0));
   std::vector<Chunk> chunks;
-  plan_chunks(B, nh, N, d, any_staged, chunks);
+  plan_chunks(B, nh, N, d, staged_kind, chunks);
   const int nc = (int)chunks.size();
   size_t max_units = 0;
   for (const Chunk& ck : chunks) max_units = std::max(max_units, (size_t)ck.nb * ck.hc);
@@ -473,9 +493,9 @@ static int run_chunks(LegacyCall& C, const fa_attn_desc& a, std::vector<Xfer>& i
   std::vector<size_t> in_off(ins.size(), 0), out_off(outs.size(), 0);
   size_t in_slot = 0, out_slot = 0;
   for (size_t i = 0; i < ins.size(); ++i)
-    if (!ins[i].direct) in_off[i] = in_slot, in_slot += (max_units * ins[i].unit * wire_bytes(ins[i].wire) + 255) & ~(size_t)255;
+    if (ins[i].ever_staged()) in_off[i] = in_slot, in_slot += (max_units * ins[i].unit * wire_bytes(ins[i].wire) + 255) & ~(size_t)255;
   for (size_t i = 0; i < outs.size(); ++i)
-    if (!outs[i].direct)
+    if (outs[i].ever_staged())
       out_off[i] = out_slot, out_slot += (max_units * outs[i].unit * wire_bytes(outs[i].wire) + 255) & ~(size_t)255;
   if ((in_slot && !P.rin.ensure(in_slot)) || (out_slot && !P.rout.ensure(out_slot)))
     return set_error(FA_ERR_CUDA, "legacy flash attention: pinned staging allocation failed (%zu + %zu bytes per slot)",
@@ -488,23 +508,23 @@ static int run_chunks(LegacyCall& C, const fa_attn_desc& a, std::vector<Xfer>& i
     const size_t u0 = (size_t)ck.b * nh + ck.h0, nu = (size_t)ck.nb * ck.hc;
     const int s = c % RS;
     if (in_slot) C.step(P.rin.acquire(s));
-    for (size_t i = 0; i < ins.size(); ++i) C.step(xfer_in(P, ins[i], u0, nu, in_slot ? P.rin.slot(s) + in_off[i] : nullptr));
+    for (size_t i = 0; i < ins.size(); ++i) C.step(xfer_in(P, ins[i], c, u0, nu, in_slot ? P.rin.slot(s) + in_off[i] : nullptr));
     if (in_slot) C.step(P.rin.mark(s, P.in));
     C.step(cudaEventRecord(P.ev_in[c], P.in));
     C.step(cudaStreamWaitEvent(P.comp, P.ev_in[c], 0));
-    for (size_t i = 0; i < ins.size() && rc == FA_OK; ++i) rc = xfer_in_cast(ins[i], u0, nu, P.comp);
+    for (size_t i = 0; i < ins.size() && rc == FA_OK; ++i) rc = xfer_in_cast(ins[i], c, u0, nu, P.comp);
     fa_attn_desc ca = a;
     ca.B = ck.nb, ca.H = ck.hc;
     if (a.kv_len) ca.kv_len = a.kv_len + ck.b;
     if (a.key_mask) ca.key_mask = a.key_mask + (size_t)ck.b * N;
     if (rc == FA_OK) rc = kernels(ca, u0);
-    for (size_t i = 0; i < outs.size() && rc == FA_OK; ++i) rc = xfer_out_cast(outs[i], u0, nu, P.comp);
+    for (size_t i = 0; i < outs.size() && rc == FA_OK; ++i) rc = xfer_out_cast(outs[i], c, u0, nu, P.comp);
     if (rc != FA_OK) break;
     C.step(cudaEventRecord(P.ev_comp[c], P.comp));
     C.step(cudaStreamWaitEvent(P.out, P.ev_comp[c], 0));
     // (slot s of the output ring was drained RS chunks ago -- see below -- so it is free)
     for (size_t i = 0; i < outs.size(); ++i)
-      C.step(xfer_out(P, outs[i], u0, nu, out_slot ? P.rout.slot(s) + out_off[i] : nullptr, s));
+      C.step(xfer_out(P, outs[i], c, u0, nu, out_slot ? P.rout.slot(s) + out_off[i] : nullptr, s));
     if (out_slot) {
       C.step(P.rout.mark(s, P.out));
       ++issued;
@@ -531,12 +551,62 @@ static int run_chunks(LegacyCall& C, const fa_attn_desc& a, std::vector<Xfer>& i
 static bool make_xfer(LegacyCall& C, Xfer& x, float* host, void* dev, size_t unit, size_t units, int wire) {
   x.host = host, x.dev = static_cast<char*>(dev), x.unit = unit, x.wire = wire;
   x.direct = use_direct(host, units * unit * 4);
+  x.staged_q = x.direct ? 0 : 4;
   x.dev32 = nullptr;
-  if (x.direct && wire == WIRE_BF16) {
-    x.dev32 = static_cast<float*>(C.temp(units * unit * 4));
-    if (!x.dev32) return false;
-  }
   return true;
+}
+// The device fp32 images of the tensors that take the direct route in bf16 mode (after plan_hybrid()).
+static bool alloc_images(LegacyCall& C, std::vector<Xfer>& xs, size_t units) {
+  for (Xfer& x : xs)
+    if (x.ever_direct() && x.wire == WIRE_BF16 && !x.dev32) {
+      x.dev32 = static_cast<float*>(C.temp(units * x.unit * 4));
+      if (!x.dev32) return false;
+    }
+  return true;
+}
+// Cost of pushing one tensor through the staging threads relative to sending it DIRECT as fp32 (measured on the
+// 16-core B200 host: about 8 ms against 10 ms for a 537 MB tensor), scaled by the threads this process may use.
+// MINITORCH_FA_HYBRID=0 switches the hybrid off; MINITORCH_FA_HYBRID_COST overrides the ratio.
+static double g_hybrid_cost = 0;                       // fa_set_transfer_policy: 0 = environment / default, < 0 = off
+static size_t g_hybrid_min_bytes = (size_t)32 << 20;   // tensors below this stay on one route
+static double hybrid_cpu_cost() {
+  if (g_hybrid_cost < 0) return -1.0;
+  if (g_hybrid_cost > 0) return g_hybrid_cost;        // (explicit: taken as is, not scaled by the thread count)
+  static const double base = [] {
+    const char* off = getenv("MINITORCH_FA_HYBRID");
+    if (off && atoi(off) == 0) return -1.0;
+    const char* e = getenv("MINITORCH_FA_HYBRID_COST");
+    return e ? atof(e) : 0.8;
+  }();
+  if (base <= 0) return -1.0;
+  return base * 16.0 / std::max(1, HostWorkers::get().threads());
+}
+// Moves quarter-tensors of the page-locked bf16-mode tensors from the DMA engine to the staging threads while that
+// shortens the call: time per direction = direct tensors x 1 + staged x 0.5 (half the bytes), host time = staged x cost.
+static void plan_hybrid(std::vector<Xfer>& ins, std::vector<Xfer>& outs, size_t units) {
+  const double cost = hybrid_cpu_cost();
+  if (cost <= 0) return;
+  auto big = [&](const Xfer& x) { return x.wire == WIRE_BF16 && units * x.unit * 4 >= g_hybrid_min_bytes; };
+  double t[2] = {0, 0}, cpu = 0;     // in units of "one big tensor, direct"
+  std::vector<Xfer>* dirs[2] = {&ins, &outs};
+  for (int k = 0; k < 2; ++k)
+    for (const Xfer& x : *dirs[k]) {
+      if (!big(x)) continue;
+      t[k] += x.staged_q == 4 ? 0.5 : 1.0;
+      if (x.staged_q == 4) cpu += cost;
+    }
+  for (;;) {
+    const int k = t[0] >= t[1] ? 0 : 1;
+    Xfer* cand = nullptr;
+    for (Xfer& x : *dirs[k])
+      if (big(x) && x.direct && x.staged_q < 4 && (!cand || x.staged_q > cand->staged_q)) cand = &x;   // fill one tensor first
+    if (!cand) break;
+    const double now = std::max(std::max(t[0], t[1]), cpu);
+    const double t_k = t[k] - 0.125, cpu2 = cpu + cost / 4;
+    if (std::max(std::max(t_k, t[1 - k]), cpu2) >= now) break;
+    ++cand->staged_q;
+    t[k] = t_k, cpu = cpu2;
+  }
 }
 
 // Common driver of the four legacy forward entry points.
@@ -583,6 +653,10 @@ static void legacy_forward(float* Q, float* K, float* V, float* O, float* l, flo
   for (int i = 0; i < 3 && ok; ++i) ok = make_xfer(C, ins[i], hin[i], E.dptr[i], ND, units, wire);
   ok = ok && make_xfer(C, outs[0], O, E.dptr[3], ND, units, wire) && make_xfer(C, outs[1], m, E.dptr[4], N, units, WIRE_F32) &&
        make_xfer(C, outs[2], l, E.dptr[5], N, units, WIRE_F32);
+  if (ok) {
+    plan_hybrid(ins, outs, units);
+    ok = alloc_images(C, ins, units) && alloc_images(C, outs, units);
+  }
   if (!ok) {
     set_error(FA_ERR_CUDA, "launch_flashattention_forward: device allocation failed");
     C.free_temps(P.in);
@@ -711,6 +785,10 @@ static void legacy_backward(float* Q, float* K, float* V, float* O, float* dQ, f
   }
   float* const hout[3] = {dQ, dK, dV};
   for (int i = 0; i < 3 && ok; ++i) ok = make_xfer(C, outs[i], hout[i], g[1 + i], ND, units, wire);
+  if (ok) {
+    plan_hybrid(ins, outs, units);
+    ok = alloc_images(C, ins, units) && alloc_images(C, outs, units);
+  }
   if (!ok) {
     set_error(FA_ERR_CUDA, "launch_flashattention_backward: device allocation failed");
     C.free_temps(P.in);

@@ -126,11 +126,30 @@ def test_pinned_and_pageable_caller_buffers_give_identical_results(lib):
         assert p
         return p, np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(count,))
 
+    def wire():
+        a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        lib.fa_wire_bytes(ctypes.byref(a), ctypes.byref(b))
+        return a.value + b.value
+
     pageable = run(lambda count: (None, np.zeros(count, dtype=np.float32)))
+    w0 = wire()
     locked = run(pinned)
-    for k in ("O", "l", "m", "dK", "dV"):
-        np.testing.assert_array_equal(pageable[k], locked[k], err_msg=k)
-    assert maxabs(pageable["dQ"], locked["dQ"]) <= 2.0 ** -7 * max(1.0, float(np.abs(locked["dQ"]).max()))
+    w1 = wire()
+    # page-locked tensors SPLIT between the two routes chunk by chunk (the policy that large tensors get by default,
+    # forced onto these small ones): the conversions on the host and on the device round alike, so the bits are the same
+    try:
+        mixed = {}
+        for cost in (0.3, 0.8, 2.0):
+            lib.fa_set_transfer_policy(cost, 0)
+            w2 = wire()
+            mixed[cost] = run(pinned)
+            assert wire() - w2 < w1 - w0, "no tensor took the bf16 route"
+    finally:
+        lib.fa_set_transfer_policy(0.0, -1)
+    for other in [locked] + list(mixed.values()):
+        for k in ("O", "l", "m", "dK", "dV"):
+            np.testing.assert_array_equal(pageable[k], other[k], err_msg=k)
+        assert maxabs(pageable["dQ"], other["dQ"]) <= 2.0 ** -7 * max(1.0, float(np.abs(locked["dQ"]).max()))
     Q, K, V, dO = (R.round_bf16(data[k]).reshape(B, H, N, d) for k in ("Q", "K", "V", "dO"))
     Oe, _, _ = R.attention_fwd(Q, K, V, causal=True)
     assert maxabs(locked["O"].reshape(B, H, N, d), Oe) < 2e-2
