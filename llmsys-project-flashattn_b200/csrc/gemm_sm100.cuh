@@ -48,6 +48,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// c ? a : b on 64-bit values, opaque to the optimiser (which otherwise turns a chain of selects over kernel parameters
+// back into an indexed load from a stack copy of them)
+__device__ __forceinline__ uint64_t sel64(uint64_t b, uint64_t a, bool c) {
+  uint64_t r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.b64 %0, %1, %2, p;\n\t}" : "=l"(r) : "l"(a), "l"(b), "r"(static_cast<int>(c)));
+  return r;
+}
+
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -190,6 +198,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           j = col0 / p.n_split;
           cj = col0 - j * p.n_split;
         }
+        // (selected with constant indices: `p.out[j]` with a run-time j makes the compiler copy the kernel parameters to
+        // a local-memory stack frame and re-load the pointer from it for every store -- ncu showed the epilogue warps
+        // stalled ~300 clk per store group on exactly those loads, 2600 clk per 32-column piece)
+        char* const outp = reinterpret_cast<char*>(
+            sel64(sel64(reinterpret_cast<uint64_t>(p.out[2]), reinterpret_cast<uint64_t>(p.out[1]), j == 1),
+                  reinterpret_cast<uint64_t>(p.out[0]), j == 0));
         const int valid = min(32, p.N - col0);      // (<= 0 when the piece is past the last column)
         if ((p.ldo & 3) == 0 && (cj & 3) == 0 && (valid & 3) == 0) {
           // Coalesced path: the accumulator arrives with lane = row; a per-warp shared-memory transpose turns it into
@@ -210,10 +224,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const int grow = m0 + warp * 32 + r;
             if (grow < p.M && cq < valid) {
               if (p.out_bf16) {
-                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out[j]) + static_cast<long long>(grow) * p.ldo + cj + cq;
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(outp) + static_cast<long long>(grow) * p.ldo + cj + cq;
                 *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
               } else {
-                float* dst = static_cast<float*>(p.out[j]) + static_cast<long long>(grow) * p.ldo + cj + cq;
+                float* dst = reinterpret_cast<float*>(outp) + static_cast<long long>(grow) * p.ldo + cj + cq;
                 *reinterpret_cast<float4*>(dst) = v;
               }
             }
@@ -222,11 +236,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         } else if (row < p.M && valid > 0) {
           // ragged / unaligned outputs: element-wise stores, lane = row
           if (p.out_bf16) {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out[j]) + static_cast<long long>(row) * p.ldo + cj;
-            for (int i = 0; i < valid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(u[i]));
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(outp) + static_cast<long long>(row) * p.ldo + cj;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)      // (predicated, fully unrolled: a run-time index would spill u[] to local memory)
+              if (i < valid) dst[i] = __float2bfloat16_rn(__uint_as_float(u[i]));
           } else {
-            float* dst = static_cast<float*>(p.out[j]) + static_cast<long long>(row) * p.ldo + cj;
-            for (int i = 0; i < valid; ++i) dst[i] = __uint_as_float(u[i]);
+            float* dst = reinterpret_cast<float*>(outp) + static_cast<long long>(row) * p.ldo + cj;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < valid) dst[i] = __uint_as_float(u[i]);
           }
         }
       }
