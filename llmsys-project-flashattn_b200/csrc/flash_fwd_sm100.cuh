@@ -92,7 +92,11 @@ __device__ __forceinline__ void store_row32_upto(OutT* dst, const float* v, int 
   if (valid >= 32) {
     store_row32<OutT>(dst, v);
   } else {
-    for (int i = 0; i < valid; ++i) dst[i] = static_cast<OutT>(v[i]);
+    // (fully unrolled and predicated: a run-time index would force the caller's register array into local memory --
+    // for the full-width path too, since both read the same array)
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < valid) dst[i] = static_cast<OutT>(v[i]);
   }
 }
 
