@@ -51,3 +51,24 @@ layer = fb.MultiHeadAttention(64, 2, causal=True, p_dropout=0.0, bias=True, back
 x = D(rng.standard_normal((2, 33, 64)), True)
 layer(x).sum().backward()
 print("device-resident ops ok", float(np.abs(x.grad.to_numpy()).max()))
+# tcgen05 GEMM (coalesced and ragged epilogues, both output dtypes) and split-KV decode attention
+import ctypes
+cl = fb._lib.load("combine")
+for (M, N, K, obf, pad) in ((200, 304, 136, 0, 0), (130, 296, 72, 0, 1), (256, 512, 64, 1, 0), (100, 88, 40, 1, 3)):
+    a_ = dev.DeviceArray.from_numpy(rng.standard_normal((M, K)).astype(np.float32), "bf16")
+    b_ = dev.DeviceArray.from_numpy(rng.standard_normal((K, N)).astype(np.float32), "bf16")
+    o_ = dev.DeviceArray((M, N + pad), "bf16" if obf else "f32")     # pad != 0: row stride not a multiple of 4 -> ragged stores
+    fb._lib.check(cl, cl.fa_gemm_bf16_dev(o_.ptr, obf, N + pad, a_.ptr, 0, K, b_.ptr, 1, N, M, N, K, None))
+    dev.sync()
+    print("gemm", (M, N, K, obf, pad), "ok", float(np.abs(o_.to_numpy()[:, :N]).max()))
+for dt, (B, H, L, d) in (("f32", (2, 3, 700, 64)), ("bf16", (1, 2, 3000, 128)), ("bf16", (3, 1, 50, 40))):
+    q = dev.DeviceArray.from_numpy(rng.standard_normal((B, H, d)).astype(np.float32), dt)
+    kc = dev.DeviceArray.from_numpy(rng.standard_normal((B, H, L, d)).astype(np.float32), dt)
+    vc = dev.DeviceArray.from_numpy(rng.standard_normal((B, H, L, d)).astype(np.float32), dt)
+    o = dev.DeviceArray((B, H, d), dt)
+    dd = fb._lib.fa_decode_desc()
+    dd.B, dd.H, dd.d, dd.L, dd.L_cap = B, H, d, L - 3, L
+    dd.dtype = fb._lib.FA_DTYPE_BF16 if dt == "bf16" else fb._lib.FA_DTYPE_F32
+    fb._lib.check(lib, lib.fa_flash_decode_dev(ctypes.byref(dd), q.ptr, kc.ptr, vc.ptr, o.ptr, None, None))
+    dev.sync()
+    print("decode", dt, (B, H, L, d), "ok", float(np.abs(o.to_numpy()).max()))
