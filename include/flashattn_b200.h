@@ -96,6 +96,10 @@ void fa_wire_bytes(unsigned long long* h2d, unsigned long long* d2h);
  * (> 0: used as given; 0: MINITORCH_FA_HYBRID_COST or the built-in 0.8 scaled by 16 / staging threads; < 0: no split,
  * page-locked tensors always go direct).  Tensors smaller than min_tensor_bytes (< 0: the default 32 MiB) are never split. */
 void fa_set_transfer_policy(double host_cost, long long min_tensor_bytes);
+/* The split a legacy call with n_in uploaded / n_out downloaded large tensors would get at host_cost (pageable[i] != 0:
+ * tensor i is pageable, i.e. staged throughout): quarters of each tensor on the staged route, 0..4.  Host logic only. */
+int fa_plan_transfer_preview(int n_in, const int* in_pageable, int n_out, const int* out_pageable, double host_cost,
+                             int* in_staged_q, int* out_staged_q);
 /* Release the pinned staging rings and the cached forward tensors of the current device. */
 int fa_release_staging(void);
 

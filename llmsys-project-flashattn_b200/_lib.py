@@ -84,6 +84,8 @@ SYMBOLS = {
         "fa_forward_cache_stats": (None, [POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),
         "fa_staging_fallbacks": (ctypes.c_ulonglong, []),
         "fa_set_transfer_policy": (None, [ctypes.c_double, c_longlong]),
+        "fa_plan_transfer_preview": (c_int, [c_int, POINTER(c_int), c_int, POINTER(c_int), ctypes.c_double, POINTER(c_int),
+                                             POINTER(c_int)]),
         "fa_wire_bytes": (None, [POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]),
         "fa_release_staging": (c_int, []),
         "launch_flashattention_forward": (None, _HOST4),

@@ -606,6 +606,29 @@ void fa_set_transfer_policy(double host_cost, long long min_tensor_bytes) {
   g_hybrid_cost = host_cost;
   g_hybrid_min_bytes = min_tensor_bytes < 0 ? ((size_t)32 << 20) : (size_t)min_tensor_bytes;
 }
+// The split plan_hybrid() would choose for a call with n_in uploaded and n_out downloaded large bf16-mode tensors
+// (pageable[i] != 0: that tensor is pageable and must go through the staging threads) at the given host cost:
+// writes the quarters of each tensor that take the staged route (0..4).  Pure host logic, no CUDA call.
+int fa_plan_transfer_preview(int n_in, const int* in_pageable, int n_out, const int* out_pageable, double host_cost,
+                             int* in_staged_q, int* out_staged_q) {
+  if (n_in < 0 || n_out < 0 || n_in > 16 || n_out > 16 || (n_in && (!in_pageable || !in_staged_q)) ||
+      (n_out && (!out_pageable || !out_staged_q)))
+    return set_error(FA_ERR_INVALID, "fa_plan_transfer_preview: bad arguments");
+  std::vector<Xfer> ins(n_in), outs(n_out);
+  const size_t unit = (size_t)64 << 20;     // one unit per tensor, far above the split threshold
+  auto fill = [&](std::vector<Xfer>& xs, const int* pageable) {
+    for (size_t i = 0; i < xs.size(); ++i) {
+      xs[i].unit = unit, xs[i].wire = WIRE_BF16;
+      xs[i].direct = !pageable[i];
+      xs[i].staged_q = pageable[i] ? 4 : 0;
+    }
+  };
+  fill(ins, in_pageable), fill(outs, out_pageable);
+  plan_hybrid(ins, outs, 1, host_cost);
+  for (int i = 0; i < n_in; ++i) in_staged_q[i] = ins[i].staged_q;
+  for (int i = 0; i < n_out; ++i) out_staged_q[i] = outs[i].staged_q;
+  return FA_OK;
+}
 void fa_wire_bytes(unsigned long long* h2d, unsigned long long* d2h) {
   if (h2d) *h2d = g_wire_h2d.load();
   if (d2h) *d2h = g_wire_d2h.load();

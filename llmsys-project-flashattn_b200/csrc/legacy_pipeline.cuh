@@ -583,8 +583,7 @@ static double hybrid_cpu_cost() {
 }
 // Moves quarter-tensors of the page-locked bf16-mode tensors from the DMA engine to the staging threads while that
 // shortens the call: time per direction = direct tensors x 1 + staged x 0.5 (half the bytes), host time = staged x cost.
-static void plan_hybrid(std::vector<Xfer>& ins, std::vector<Xfer>& outs, size_t units) {
-  const double cost = hybrid_cpu_cost();
+static void plan_hybrid(std::vector<Xfer>& ins, std::vector<Xfer>& outs, size_t units, double cost) {
   if (cost <= 0) return;
   auto big = [&](const Xfer& x) { return x.wire == WIRE_BF16 && units * x.unit * 4 >= g_hybrid_min_bytes; };
   double t[2] = {0, 0}, cpu = 0;     // in units of "one big tensor, direct"
@@ -607,6 +606,9 @@ static void plan_hybrid(std::vector<Xfer>& ins, std::vector<Xfer>& outs, size_t 
     ++cand->staged_q;
     t[k] = t_k, cpu = cpu2;
   }
+}
+static void plan_hybrid(std::vector<Xfer>& ins, std::vector<Xfer>& outs, size_t units) {
+  plan_hybrid(ins, outs, units, hybrid_cpu_cost());
 }
 
 // Common driver of the four legacy forward entry points.
