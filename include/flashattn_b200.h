@@ -85,7 +85,8 @@ void fa_set_legacy_chunk_bytes(size_t bytes);
  * MINITORCH_FA_KEEP_FWD_MB; 0 disables): oldest entries are dropped first, a backward consumes its entry. */
 void fa_set_keep_forward_mb(long long mb);
 void fa_forward_cache_stats(unsigned long long* hits, unsigned long long* misses);
-/* Times a pinned staging ring could not be allocated and a call fell back to direct (slow, pageable) copies. */
+/* Times a pinned staging ring could not be allocated (the call that needed it failed with FA_ERR_CUDA and said so;
+ * fa_release_staging() or a smaller MINITORCH_FA_CHUNK_MB frees / needs less page-locked memory). */
 unsigned long long fa_staging_fallbacks(void);
 /* Bytes the legacy entry points have handed to the DMA engine since the library was loaded, per direction.  In bf16 mode
  * a page-locked caller tensor is split between two routes -- fp32 image by DMA + cast on the device, or narrowed /

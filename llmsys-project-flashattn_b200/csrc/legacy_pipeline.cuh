@@ -151,7 +151,7 @@ static bool is_pageable(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------------ per-device state
-static unsigned long long g_staging_fallbacks = 0;   // pinned ring could not be allocated -> direct (slow) copies
+static unsigned long long g_staging_fallbacks = 0;   // times a pinned ring could not be allocated (the call then fails loudly)
 static std::atomic<unsigned long long> g_wire_h2d{0}, g_wire_d2h{0};   // bytes handed to the DMA engine (fa_wire_bytes)
 
 struct PinnedRing {
