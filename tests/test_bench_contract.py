@@ -82,3 +82,18 @@ def test_committed_bench_lines_carry_the_contract(path):
     else:
         assert len(d["per_rank_ms"]["step"]) == d["n_gpus"]
         assert abs(max(d["per_rank_ms"]["step"]) - d["ms_per_step"]) < 1e-6      # max over ranks
+
+
+@pytest.mark.timeout(900)
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches the reference arm like the product arm (torchrun, one process per GPU): rank 0 alone
+    measures and prints, the other ranks exit 0 without work."""
+    env = dict(os.environ, NUMBA_DISABLE_CUDA="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=850, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = _json_lines(r.stdout)
+    assert len(lines) == 1
+    assert lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2 and lines[0]["value"] > 0
